@@ -1,0 +1,581 @@
+// C ABI of libnbody_b200.so (include/nbody_b200.h): context, body upload, operator entry points, read-back,
+// tree export for the parity tests.  No CPU fallback anywhere: every compute entry point launches sm_100a kernels.
+#include <math.h>
+#include <stdarg.h>
+#include <string.h>
+
+#include <algorithm>
+#include <vector>
+
+#include "common.cuh"
+
+int nbk_comm_allreduce_sum(nb_ctx *ctx, double *buf, size_t count);
+
+int nb_fail(nb_ctx *ctx, int status, const char *fmt, ...) {
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    if (ctx) ctx->last_error = buf;
+    return status;
+}
+
+static thread_local std::string g_create_error;
+
+extern "C" {
+
+int nb_abi_version(void) { return NB_ABI_VERSION; }
+
+const char *nb_status_string(int s) {
+    switch (s) {
+        case NB_OK: return "ok";
+        case NB_ERR_INVALID: return "invalid argument";
+        case NB_ERR_NO_DEVICE: return "no usable CUDA device (no CPU fallback)";
+        case NB_ERR_CUDA: return "CUDA error";
+        case NB_ERR_TREE_DEPTH: return "octree deeper than 42 levels (coincident bodies)";
+        case NB_ERR_NODE_POOL: return "octree node pool overflow (raise storage_size_param)";
+        case NB_ERR_COMM: return "NCCL error";
+        case NB_ERR_UNSUPPORTED: return "unsupported";
+        default: return "unknown";
+    }
+}
+
+void nb_config_default(nb_config *c) {
+    memset(c, 0, sizeof *c);
+    c->struct_size = sizeof(nb_config);
+    c->device = 0;
+    // nBodyAlgorithm.hpp:55-61
+    double G = 6.67428 * pow(10, -11);
+    double meter_AU = 1.0 / (1.49597870691 * pow(10, 11));
+    double second_Days = 1.0 / 86400;
+    c->G = G * (pow(meter_AU, 3) / pow(second_Days, 2));
+    c->epsilon2 = pow(10, -22);  // Configuration.cpp:6
+    c->theta = 1.05;             // :18
+    c->block_size = 64;          // :10
+    c->opt_stage = 2;            // :11
+    c->sort_bodies = 1;          // :21
+    c->wg_size_barnes_hut = 64;  // :22
+    c->storage_size_param = 16;  // main.cpp:122-127
+    c->stack_size_param = 16;    // main.cpp:129-134
+    c->num_wi_aabb = 1024;       // :14
+    c->num_wi_octree = 640;      // :15
+    c->num_wi_top_octree = 1024; // :16
+    c->num_wi_com = 1024;        // :17
+    c->max_level_top_octree = 7; // :19
+    c->precise_rsqrt = 1;
+    c->world_size = 1;
+    c->rank = 0;
+}
+
+int nb_create(const nb_config *cfg, nb_ctx **out) {
+    if (!cfg || !out || cfg->struct_size != sizeof(nb_config)) return NB_ERR_INVALID;
+    if (cfg->opt_stage < 0 || cfg->opt_stage > 2) return NB_ERR_INVALID;  // main.cpp:154-157
+    int count = 0;
+    if (cudaGetDeviceCount(&count) != cudaSuccess || count <= 0 || cfg->device >= count) return NB_ERR_NO_DEVICE;
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, cfg->device) != cudaSuccess) return NB_ERR_NO_DEVICE;
+    if (prop.major < 10) return NB_ERR_NO_DEVICE;  // kernels are compiled for sm_100a only
+    nb_ctx *ctx = new nb_ctx();
+    ctx->cfg = *cfg;
+    ctx->device = cfg->device;
+    ctx->sm_count = prop.multiProcessorCount;
+    ctx->device_name = prop.name;
+    ctx->world = cfg->world_size > 0 ? cfg->world_size : 1;
+    ctx->rank = cfg->rank;
+    if (cudaSetDevice(ctx->device) != cudaSuccess ||
+        cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) {
+        delete ctx;
+        return NB_ERR_CUDA;
+    }
+    for (int i = 0; i < 2 * NB_T_COUNT; ++i) cudaEventCreate(&ctx->ev[i]);
+    *out = ctx;
+    return NB_OK;
+}
+
+void nb_destroy(nb_ctx *ctx) {
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    cudaStreamSynchronize(ctx->stream);
+    nbk_comm_destroy(ctx);
+    nbk_bh_release(ctx);
+    nb_free(&ctx->m); nb_free(&ctx->x); nb_free(&ctx->y); nb_free(&ctx->z);
+    nb_free(&ctx->vx); nb_free(&ctx->vy); nb_free(&ctx->vz);
+    nb_free(&ctx->ax); nb_free(&ctx->ay); nb_free(&ctx->az);
+    nb_free(&ctx->anorm); nb_free(&ctx->src); nb_free(&ctx->e_partial);
+    if (ctx->h_pinned) cudaFreeHost(ctx->h_pinned);
+    for (int i = 0; i < 2 * NB_T_COUNT; ++i) cudaEventDestroy(ctx->ev[i]);
+    cudaStreamDestroy(ctx->stream);
+    delete ctx;
+}
+
+const char *nb_last_error(const nb_ctx *ctx) { return ctx ? ctx->last_error.c_str() : "null context"; }
+
+static int check_bh_flags(nb_ctx *ctx);
+
+int nb_synchronize(nb_ctx *ctx) {
+    if (!ctx) return NB_ERR_INVALID;
+    NB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return check_bh_flags(ctx);
+}
+
+int nb_device_name(nb_ctx *ctx, char *buf, size_t buflen) {
+    if (!ctx || !buf || !buflen) return NB_ERR_INVALID;
+    snprintf(buf, buflen, "%s", ctx->device_name.c_str());
+    return NB_OK;
+}
+
+int nb_set_theta(nb_ctx *ctx, double theta) { if (!ctx) return NB_ERR_INVALID; ctx->cfg.theta = theta; return NB_OK; }
+int nb_set_block_size(nb_ctx *ctx, int bs) { if (!ctx || bs <= 0) return NB_ERR_INVALID; ctx->cfg.block_size = bs; return NB_OK; }
+int nb_set_sort_bodies(nb_ctx *ctx, int s) { if (!ctx) return NB_ERR_INVALID; ctx->cfg.sort_bodies = s; return NB_OK; }
+int nb_set_precise_rsqrt(nb_ctx *ctx, int p) { if (!ctx) return NB_ERR_INVALID; ctx->cfg.precise_rsqrt = p; return NB_OK; }
+
+uint64_t nb_num_bodies(const nb_ctx *ctx) { return ctx ? ctx->n : 0; }
+uint64_t nb_launch_count(const nb_ctx *ctx) { return ctx ? ctx->launches : 0; }
+
+static int ensure_capacity(nb_ctx *ctx, uint64_t n) {
+    // arrays that take part in the in-place all-gather need world * ceil(n/world) elements
+    const uint64_t chunk = (n + ctx->world - 1) / ctx->world;
+    const uint64_t need = chunk * ctx->world + 32;
+    if (need <= ctx->cap) return NB_OK;
+    NB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    NB_CHECK(nb_alloc(ctx, &ctx->m, need));
+    NB_CHECK(nb_alloc(ctx, &ctx->x, need));
+    NB_CHECK(nb_alloc(ctx, &ctx->y, need));
+    NB_CHECK(nb_alloc(ctx, &ctx->z, need));
+    NB_CHECK(nb_alloc(ctx, &ctx->vx, need));
+    NB_CHECK(nb_alloc(ctx, &ctx->vy, need));
+    NB_CHECK(nb_alloc(ctx, &ctx->vz, need));
+    NB_CHECK(nb_alloc(ctx, &ctx->ax, need));
+    NB_CHECK(nb_alloc(ctx, &ctx->ay, need));
+    NB_CHECK(nb_alloc(ctx, &ctx->az, need));
+    NB_CHECK(nb_alloc(ctx, &ctx->anorm, need));
+    NB_CHECK(nb_alloc(ctx, &ctx->e_partial, 2 * need + 8 + 2048));
+    ctx->cap = need;
+    return NB_OK;
+}
+
+static int h2d(nb_ctx *ctx, double *dst, const double *src, uint64_t n) {
+    if (!src) return NB_OK;
+    NB_CUDA(ctx, cudaMemcpyAsync(dst, src, n * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+    return NB_OK;
+}
+static int d2h(nb_ctx *ctx, double *dst, const double *src, uint64_t n) {
+    if (!dst) return NB_OK;
+    NB_CUDA(ctx, cudaMemcpyAsync(dst, src, n * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    return NB_OK;
+}
+
+int nb_set_bodies(nb_ctx *ctx, uint64_t n, const double *mass, const double *x, const double *y, const double *z,
+                  const double *vx, const double *vy, const double *vz) {
+    if (!ctx) return NB_ERR_INVALID;
+    if (n == 0 || !mass || !x || !y || !z) return nb_fail(ctx, NB_ERR_INVALID, "nb_set_bodies: need n > 0 and mass/x/y/z");
+    NB_CUDA(ctx, cudaSetDevice(ctx->device));
+    NB_CHECK(ensure_capacity(ctx, n));
+    ctx->n = n;
+    ctx->bh.built = false;
+    NB_CHECK(h2d(ctx, ctx->m, mass, n));
+    NB_CHECK(h2d(ctx, ctx->x, x, n));
+    NB_CHECK(h2d(ctx, ctx->y, y, n));
+    NB_CHECK(h2d(ctx, ctx->z, z, n));
+    if (vx && vy && vz) {
+        NB_CHECK(h2d(ctx, ctx->vx, vx, n));
+        NB_CHECK(h2d(ctx, ctx->vy, vy, n));
+        NB_CHECK(h2d(ctx, ctx->vz, vz, n));
+    } else {
+        NB_CUDA(ctx, cudaMemsetAsync(ctx->vx, 0, n * sizeof(double), ctx->stream));
+        NB_CUDA(ctx, cudaMemsetAsync(ctx->vy, 0, n * sizeof(double), ctx->stream));
+        NB_CUDA(ctx, cudaMemsetAsync(ctx->vz, 0, n * sizeof(double), ctx->stream));
+    }
+    NB_CUDA(ctx, cudaMemsetAsync(ctx->ax, 0, n * sizeof(double), ctx->stream));
+    NB_CUDA(ctx, cudaMemsetAsync(ctx->ay, 0, n * sizeof(double), ctx->stream));
+    NB_CUDA(ctx, cudaMemsetAsync(ctx->az, 0, n * sizeof(double), ctx->stream));
+    // the host arrays are caller-owned and only valid during the call
+    NB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return NB_OK;
+}
+
+int nb_set_positions(nb_ctx *ctx, const double *x, const double *y, const double *z) {
+    if (!ctx || !ctx->n) return nb_fail(ctx, NB_ERR_INVALID, "nb_set_positions: no bodies");
+    NB_CUDA(ctx, cudaSetDevice(ctx->device));
+    NB_CHECK(h2d(ctx, ctx->x, x, ctx->n));
+    NB_CHECK(h2d(ctx, ctx->y, y, ctx->n));
+    NB_CHECK(h2d(ctx, ctx->z, z, ctx->n));
+    ctx->bh.built = false;
+    NB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return NB_OK;
+}
+
+// ---- operators -------------------------------------------------------------------------------------------------------
+int nb_naive_accel(nb_ctx *ctx) {
+    if (!ctx || !ctx->n) return nb_fail(ctx, NB_ERR_INVALID, "nb_naive_accel: no bodies");
+    NB_CUDA(ctx, cudaSetDevice(ctx->device));
+    nb_timer_scope t(ctx, NB_T_ACCEL);
+    uint64_t b = 0, e = ctx->n;
+    nb_slice_bounds(ctx->n, ctx->world, ctx->rank, &b, &e);
+    NB_CHECK(nbk_naive_accel(ctx, b, e));
+    NB_CHECK(nbk_comm_allgather_accel(ctx, ctx->ax, ctx->ay, ctx->az, ctx->n));
+    return NB_OK;
+}
+
+int nb_bh_build(nb_ctx *ctx) {
+    if (!ctx || !ctx->n) return nb_fail(ctx, NB_ERR_INVALID, "nb_bh_build: no bodies");
+    NB_CUDA(ctx, cudaSetDevice(ctx->device));
+    return nbk_bh_build(ctx);
+}
+
+int nb_bh_accel(nb_ctx *ctx) {
+    if (!ctx || !ctx->n) return nb_fail(ctx, NB_ERR_INVALID, "nb_bh_accel: no bodies");
+    NB_CUDA(ctx, cudaSetDevice(ctx->device));
+    nb_timer_scope t(ctx, NB_T_ACCEL);
+    uint64_t b = 0, e = ctx->n;
+    nb_slice_bounds(ctx->n, ctx->world, ctx->rank, &b, &e);
+    NB_CHECK(nbk_bh_accel(ctx, b, e));
+    NB_CHECK(nbk_comm_allgather_accel(ctx, ctx->bh.asx, ctx->bh.asy, ctx->bh.asz, ctx->n));
+    NB_CHECK(nbk_bh_scatter_accel(ctx));
+    return NB_OK;
+}
+
+int nb_leapfrog_part1(nb_ctx *ctx, double dt) {
+    if (!ctx) return NB_ERR_INVALID;
+    NB_CUDA(ctx, cudaSetDevice(ctx->device));
+    nb_timer_scope t(ctx, NB_T_LEAPFROG1);
+    ctx->bh.built = false;
+    return nbk_leapfrog_part1(ctx, dt);
+}
+int nb_leapfrog_part2(nb_ctx *ctx, double dt) {
+    if (!ctx) return NB_ERR_INVALID;
+    NB_CUDA(ctx, cudaSetDevice(ctx->device));
+    nb_timer_scope t(ctx, NB_T_LEAPFROG2);
+    return nbk_leapfrog_part2(ctx, dt);
+}
+int nb_leapfrog_part2_part1(nb_ctx *ctx, double dt) {
+    if (!ctx) return NB_ERR_INVALID;
+    NB_CUDA(ctx, cudaSetDevice(ctx->device));
+    nb_timer_scope t(ctx, NB_T_LEAPFROG1);
+    ctx->bh.built = false;
+    return nbk_leapfrog_part2_part1(ctx, dt);
+}
+
+int nb_energy(nb_ctx *ctx, double out[4]) {
+    if (!ctx || !ctx->n || !out) return nb_fail(ctx, NB_ERR_INVALID, "nb_energy: no bodies");
+    NB_CUDA(ctx, cudaSetDevice(ctx->device));
+    const uint64_t n = ctx->n;
+    {
+        nb_timer_scope t(ctx, NB_T_ENERGY);
+        // triangular work: rank r takes targets [n*sqrt(r/P), n*sqrt((r+1)/P)) so pair counts balance
+        uint64_t jb = 0, je = n;
+        if (ctx->world > 1) {
+            jb = (uint64_t) floor((double) n * sqrt((double) ctx->rank / ctx->world));
+            je = ctx->rank + 1 == ctx->world ? n : (uint64_t) floor((double) n * sqrt((double) (ctx->rank + 1) / ctx->world));
+        }
+        NB_CHECK(nbk_energy(ctx, jb, je));
+        NB_CHECK(nbk_comm_allreduce_sum(ctx, ctx->e_partial + 2 * n, 2));
+    }
+    double h[2];
+    NB_CUDA(ctx, cudaMemcpyAsync(h, ctx->e_partial + 2 * n, 2 * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    NB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    // nBodyAlgorithm.cpp:77-85
+    double E_kin_result = h[0], E_pot_result = h[1];
+    E_pot_result *= -1;
+    out[0] = E_kin_result;
+    out[1] = E_pot_result;
+    out[2] = E_kin_result + E_pot_result;
+    out[3] = (2.0 * E_kin_result) / fabs(E_pot_result);
+    return NB_OK;
+}
+
+// ---- read-back ----------------------------------------------------------------------------------------------------------
+int nb_get_positions(nb_ctx *ctx, double *x, double *y, double *z) {
+    if (!ctx || !ctx->n) return nb_fail(ctx, NB_ERR_INVALID, "no bodies");
+    NB_CUDA(ctx, cudaSetDevice(ctx->device));
+    NB_CHECK(d2h(ctx, x, ctx->x, ctx->n)); NB_CHECK(d2h(ctx, y, ctx->y, ctx->n)); NB_CHECK(d2h(ctx, z, ctx->z, ctx->n));
+    return nb_synchronize(ctx);
+}
+int nb_get_velocities(nb_ctx *ctx, double *vx, double *vy, double *vz) {
+    if (!ctx || !ctx->n) return nb_fail(ctx, NB_ERR_INVALID, "no bodies");
+    NB_CUDA(ctx, cudaSetDevice(ctx->device));
+    NB_CHECK(d2h(ctx, vx, ctx->vx, ctx->n)); NB_CHECK(d2h(ctx, vy, ctx->vy, ctx->n)); NB_CHECK(d2h(ctx, vz, ctx->vz, ctx->n));
+    return nb_synchronize(ctx);
+}
+int nb_get_accelerations(nb_ctx *ctx, double *ax, double *ay, double *az) {
+    if (!ctx || !ctx->n) return nb_fail(ctx, NB_ERR_INVALID, "no bodies");
+    NB_CUDA(ctx, cudaSetDevice(ctx->device));
+    NB_CHECK(d2h(ctx, ax, ctx->ax, ctx->n)); NB_CHECK(d2h(ctx, ay, ctx->ay, ctx->n)); NB_CHECK(d2h(ctx, az, ctx->az, ctx->n));
+    return nb_synchronize(ctx);
+}
+int nb_get_acceleration_norms(nb_ctx *ctx, double *anorm) {
+    if (!ctx || !ctx->n || !anorm) return nb_fail(ctx, NB_ERR_INVALID, "no bodies");
+    NB_CUDA(ctx, cudaSetDevice(ctx->device));
+    NB_CHECK(nbk_accel_norm(ctx));
+    NB_CHECK(d2h(ctx, anorm, ctx->anorm, ctx->n));
+    return nb_synchronize(ctx);
+}
+
+int nb_device_pointers(nb_ctx *ctx, void *p[10]) {
+    if (!ctx || !p) return NB_ERR_INVALID;
+    p[0] = ctx->x; p[1] = ctx->y; p[2] = ctx->z; p[3] = ctx->vx; p[4] = ctx->vy; p[5] = ctx->vz;
+    p[6] = ctx->ax; p[7] = ctx->ay; p[8] = ctx->az; p[9] = ctx->m;
+    return NB_OK;
+}
+
+// ---- one-call operator forms with host buffers --------------------------------------------------------------------------
+static int upload_for_op(nb_ctx *ctx, uint64_t n, const double *mass, const double *x, const double *y, const double *z) {
+    if (n == 0 || !mass || !x || !y || !z) return nb_fail(ctx, NB_ERR_INVALID, "operator: need n > 0 and mass/x/y/z");
+    NB_CUDA(ctx, cudaSetDevice(ctx->device));
+    NB_CHECK(ensure_capacity(ctx, n));
+    ctx->n = n;
+    ctx->bh.built = false;
+    NB_CHECK(h2d(ctx, ctx->m, mass, n));
+    NB_CHECK(h2d(ctx, ctx->x, x, n));
+    NB_CHECK(h2d(ctx, ctx->y, y, n));
+    NB_CHECK(h2d(ctx, ctx->z, z, n));
+    return NB_OK;
+}
+
+int nb_op_naive_accelerations(nb_ctx *ctx, uint64_t n, const double *mass, const double *x, const double *y,
+                              const double *z, double *ax, double *ay, double *az) {
+    if (!ctx) return NB_ERR_INVALID;
+    NB_CHECK(upload_for_op(ctx, n, mass, x, y, z));
+    NB_CHECK(nb_naive_accel(ctx));
+    return nb_get_accelerations(ctx, ax, ay, az);
+}
+
+int nb_op_barnes_hut_accelerations(nb_ctx *ctx, uint64_t n, const double *mass, const double *x, const double *y,
+                                   const double *z, double *ax, double *ay, double *az) {
+    if (!ctx) return NB_ERR_INVALID;
+    NB_CHECK(upload_for_op(ctx, n, mass, x, y, z));
+    NB_CHECK(nb_bh_build(ctx));
+    NB_CHECK(nb_bh_accel(ctx));
+    return nb_get_accelerations(ctx, ax, ay, az);
+}
+
+// ---- timers ------------------------------------------------------------------------------------------------------------------
+int nb_enable_timers(nb_ctx *ctx, int enable) {
+    if (!ctx) return NB_ERR_INVALID;
+    ctx->timers_enabled = enable != 0;
+    return NB_OK;
+}
+int nb_get_timers(nb_ctx *ctx, double ms[NB_T_COUNT]) {
+    if (!ctx || !ms) return NB_ERR_INVALID;
+    NB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    for (int i = 0; i < NB_T_COUNT; ++i) {
+        ms[i] = 0;
+        if (ctx->ev_valid[i]) {
+            float f = 0;
+            if (cudaEventElapsedTime(&f, ctx->ev[2 * i], ctx->ev[2 * i + 1]) == cudaSuccess) ms[i] = f;
+        }
+    }
+    return NB_OK;
+}
+const char *nb_timer_name(int t) {
+    static const char *names[NB_T_COUNT] = {"Acceleration Kernel Time", "Leapfrog Part 1", "Leapfrog Part 2",
+                                            "AABB creation", "Sort bodies for subtrees", "Build subtrees",
+                                            "Compute center of mass", "Octree creation", "Energy", "Allgather"};
+    return (t >= 0 && t < NB_T_COUNT) ? names[t] : "";
+}
+
+int nb_measure_fp64_peak(nb_ctx *ctx, double *tflops) {
+    if (!ctx || !tflops) return NB_ERR_INVALID;
+    NB_CUDA(ctx, cudaSetDevice(ctx->device));
+    return nbk_fp64_peak(ctx, tflops);
+}
+
+// ---- Barnes-Hut inspection -------------------------------------------------------------------------------------------------
+static int check_bh_flags(nb_ctx *ctx) {
+    nb_bh_state &b = ctx->bh;
+    if (!b.built || !b.dev_flags) return NB_OK;
+    uint32_t f[4];
+    NB_CUDA(ctx, cudaMemcpy(f, b.dev_flags, sizeof f, cudaMemcpyDeviceToHost));
+    b.num_internal = f[1];
+    b.num_nodes = ctx->n + f[1];
+    b.max_depth = f[2];
+    if (f[0] & 2u) {
+        b.built = false;
+        return nb_fail(ctx, NB_ERR_NODE_POOL, "octree needs %llu internal nodes, pool holds %llu (storage_size_param=%d)",
+                       (unsigned long long) f[1], (unsigned long long) (b.cap_nodes - ctx->n), ctx->cfg.storage_size_param);
+    }
+    if (f[0] & 1u) {
+        b.built = false;
+        return nb_fail(ctx, NB_ERR_TREE_DEPTH, "octree deeper than %d levels: coincident bodies are not supported (reference: unbounded splitting)",
+                       NB_MAX_TREE_DEPTH);
+    }
+    return NB_OK;
+}
+
+int nb_bh_aabb(nb_ctx *ctx, double out[7]) {
+    if (!ctx || !ctx->n || !out) return nb_fail(ctx, NB_ERR_INVALID, "nb_bh_aabb: no bodies");
+    NB_CUDA(ctx, cudaSetDevice(ctx->device));
+    NB_CHECK(nbk_bh_reserve(ctx));
+    NB_CHECK(nbk_bh_aabb(ctx));
+    NB_CUDA(ctx, cudaMemcpyAsync(out, ctx->bh.aabb_dev, 7 * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    NB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return NB_OK;
+}
+
+int nb_bh_tree_info(nb_ctx *ctx, nb_tree_info *info) {
+    if (!ctx || !info) return NB_ERR_INVALID;
+    if (!ctx->bh.built) return nb_fail(ctx, NB_ERR_INVALID, "nb_bh_tree_info: no tree");
+    NB_CUDA(ctx, cudaSetDevice(ctx->device));
+    NB_CHECK(nb_synchronize(ctx));
+    nb_bh_state &b = ctx->bh;
+    NB_CUDA(ctx, cudaMemcpy(b.aabb, b.aabb_dev, 7 * sizeof(double), cudaMemcpyDeviceToHost));
+    memset(info, 0, sizeof *info);
+    info->num_bodies = ctx->n;
+    info->num_nodes_materialised = b.num_nodes;
+    info->num_internal = b.num_internal;
+    info->num_nodes_canonical = 1 + 8 * b.num_internal;
+    info->max_depth = b.max_depth;
+    for (int k = 0; k < 3; ++k) { info->aabb_min[k] = b.aabb[k]; info->aabb_max[k] = b.aabb[3 + k]; }
+    info->aabb_edge = b.aabb[6];
+    return NB_OK;
+}
+
+int nb_bh_enable_stats(nb_ctx *ctx, int enable) {
+    if (!ctx) return NB_ERR_INVALID;
+    ctx->bh.stats_enabled = enable != 0;
+    return NB_OK;
+}
+
+int nb_bh_get_stats(nb_ctx *ctx, uint64_t *total_visits, uint64_t *total_accepts, uint32_t *visits_per_body) {
+    if (!ctx || !ctx->bh.built) return nb_fail(ctx, NB_ERR_INVALID, "nb_bh_get_stats: no tree");
+    NB_CUDA(ctx, cudaSetDevice(ctx->device));
+    NB_CHECK(nb_synchronize(ctx));
+    unsigned long long t[2];
+    NB_CUDA(ctx, cudaMemcpy(t, ctx->bh.stat_totals, sizeof t, cudaMemcpyDeviceToHost));
+    if (total_visits) *total_visits = t[0];
+    if (total_accepts) *total_accepts = t[1];
+    if (visits_per_body) {
+        // device counters are in sorted order; return them by body id
+        std::vector<uint32_t> v(ctx->n), perm(ctx->n);
+        NB_CUDA(ctx, cudaMemcpy(v.data(), ctx->bh.visits, ctx->n * sizeof(uint32_t), cudaMemcpyDeviceToHost));
+        NB_CUDA(ctx, cudaMemcpy(perm.data(), ctx->bh.perm, ctx->n * sizeof(uint32_t), cudaMemcpyDeviceToHost));
+        for (uint64_t s = 0; s < ctx->n; ++s) visits_per_body[perm[s]] = v[s];
+    }
+    return NB_OK;
+}
+
+// Host-side expansion of the device tree (DFS pre-order, visit-rank child order, empty leaves implied) into the
+// reference's canonical node set.  Test / inspection path only.
+namespace {
+struct HostTree {
+    uint64_t n = 0, M = 0;
+    std::vector<uint2> meta;
+    std::vector<double> com, msum;
+    std::vector<uint32_t> first_body, body_count, perm;
+    std::vector<uint64_t> hi, lo;
+    double aabb[7];
+};
+int fetch_tree(nb_ctx *ctx, HostTree &t) {
+    nb_bh_state &b = ctx->bh;
+    NB_CHECK(nb_synchronize(ctx));
+    t.n = ctx->n;
+    t.M = b.num_nodes;
+    t.meta.resize(t.M); t.com.resize(4 * t.M); t.msum.resize(3 * t.M);
+    t.first_body.resize(t.M); t.body_count.resize(t.M); t.perm.resize(t.n); t.hi.resize(t.n); t.lo.resize(t.n);
+    NB_CUDA(ctx, cudaMemcpy(t.meta.data(), b.meta, t.M * sizeof(uint2), cudaMemcpyDeviceToHost));
+    NB_CUDA(ctx, cudaMemcpy(t.com.data(), b.com, 4 * t.M * sizeof(double), cudaMemcpyDeviceToHost));
+    NB_CUDA(ctx, cudaMemcpy(t.msum.data(), b.msum, 3 * t.M * sizeof(double), cudaMemcpyDeviceToHost));
+    NB_CUDA(ctx, cudaMemcpy(t.first_body.data(), b.first_body, t.M * sizeof(uint32_t), cudaMemcpyDeviceToHost));
+    NB_CUDA(ctx, cudaMemcpy(t.body_count.data(), b.body_count, t.M * sizeof(uint32_t), cudaMemcpyDeviceToHost));
+    NB_CUDA(ctx, cudaMemcpy(t.perm.data(), b.perm, t.n * sizeof(uint32_t), cudaMemcpyDeviceToHost));
+    NB_CUDA(ctx, cudaMemcpy(t.hi.data(), b.key_hi, t.n * sizeof(uint64_t), cudaMemcpyDeviceToHost));
+    NB_CUDA(ctx, cudaMemcpy(t.lo.data(), b.key_hi_alt, t.n * sizeof(uint64_t), cudaMemcpyDeviceToHost));
+    NB_CUDA(ctx, cudaMemcpy(t.aabb, b.aabb_dev, 7 * sizeof(double), cudaMemcpyDeviceToHost));
+    return NB_OK;
+}
+inline uint32_t host_digit(const HostTree &t, uint32_t body, int level) {
+    return level < 21 ? (uint32_t) ((t.hi[body] >> (60 - 3 * level)) & 7) : (uint32_t) ((t.lo[body] >> (60 - 3 * (level - 21))) & 7);
+}
+inline uint32_t rank_to_octant(uint32_t r) {  // rank = 4u + 2b + (1-r)  ->  octant = 4u + 2r + b
+    const uint32_t u = r >> 2, bk = (r >> 1) & 1, rt = 1 - (r & 1);
+    return 4 * u + 2 * rt + bk;
+}
+struct CanonSink {
+    uint32_t *depth; uint64_t *path_hi, *path_lo; uint32_t *kind, *body, *count;
+    double *edge, *minx, *miny, *minz, *mass, *comx, *comy, *comz;
+    size_t k = 0;
+    std::vector<uint32_t> *sorted = nullptr;
+};
+void canon_rec(const HostTree &t, uint32_t node, int depth, uint64_t phi, uint64_t plo, double edge, double mnx,
+               double mny, double mnz, CanonSink &s) {
+    const uint2 m = t.meta[node];
+    const bool leaf = (m.y & NB_LEAF_FLAG) != 0;
+    if (s.depth) {
+        const size_t k = s.k;
+        s.depth[k] = depth; s.path_hi[k] = phi; s.path_lo[k] = plo;
+        s.kind[k] = leaf ? 1 : 2;
+        s.body[k] = leaf ? t.perm[m.y & ~NB_LEAF_FLAG] : (uint32_t) t.n;
+        s.count[k] = t.body_count[node];
+        s.edge[k] = edge; s.minx[k] = mnx; s.miny[k] = mny; s.minz[k] = mnz;
+        s.mass[k] = t.com[4 * (size_t) node + 3];
+        s.comx[k] = t.msum[3 * (size_t) node]; s.comy[k] = t.msum[3 * (size_t) node + 1]; s.comz[k] = t.msum[3 * (size_t) node + 2];
+    }
+    s.k++;
+    if (leaf) {
+        if (s.sorted) s.sorted->push_back(t.perm[m.y & ~NB_LEAF_FLAG]);
+        return;
+    }
+    uint32_t child_of_octant[8];
+    for (int o = 0; o < 8; ++o) child_of_octant[o] = NB_LEAF_FLAG;  // marker: empty
+    for (uint32_t c = node + 1; c < m.x;) {
+        const uint2 mc = t.meta[c];
+        const uint32_t fb = (mc.y & NB_LEAF_FLAG) ? (mc.y & ~NB_LEAF_FLAG) : t.first_body[c];
+        child_of_octant[rank_to_octant(host_digit(t, fb, depth))] = c;
+        c = mc.x;
+    }
+    const double h = edge / 2;  // ParallelOctreeTopDownSubtrees.cpp:256
+    for (uint64_t o = 0; o < 8; ++o) {
+        uint64_t h2 = phi, l2 = plo;
+        if (depth < 21) h2 |= o << (60 - 3 * depth);
+        else if (depth < 42) l2 |= o << (60 - 3 * (depth - 21));
+        // child bounds :277-315: +h in y for bit 2, +h in x for bit 1, +h in z when bit 0 is CLEAR
+        const double cx = (o & 2) ? mnx + h : mnx;
+        const double cy = (o & 4) ? mny + h : mny;
+        const double cz = (o & 1) ? mnz : mnz + h;
+        if (child_of_octant[o] == NB_LEAF_FLAG) {
+            if (s.depth) {
+                const size_t k = s.k;
+                s.depth[k] = depth + 1; s.path_hi[k] = h2; s.path_lo[k] = l2;
+                s.kind[k] = 0; s.body[k] = (uint32_t) t.n; s.count[k] = 0;
+                s.edge[k] = h; s.minx[k] = cx; s.miny[k] = cy; s.minz[k] = cz;
+                s.mass[k] = 0; s.comx[k] = 0; s.comy[k] = 0; s.comz[k] = 0;
+            }
+            s.k++;
+        } else {
+            canon_rec(t, child_of_octant[o], depth + 1, h2, l2, h, cx, cy, cz, s);
+        }
+    }
+}
+}  // namespace
+
+int nb_bh_export_canonical(nb_ctx *ctx, uint32_t *depth, uint64_t *path_hi, uint64_t *path_lo, uint32_t *kind,
+                           uint32_t *body, uint32_t *count, double *edge, double *minx, double *miny, double *minz,
+                           double *mass, double *comx, double *comy, double *comz) {
+    if (!ctx || !ctx->bh.built) return nb_fail(ctx, NB_ERR_INVALID, "nb_bh_export_canonical: no tree");
+    if (!depth || !path_hi || !path_lo || !kind || !body || !count || !edge || !minx || !miny || !minz || !mass ||
+        !comx || !comy || !comz)
+        return nb_fail(ctx, NB_ERR_INVALID, "nb_bh_export_canonical: null output");
+    NB_CUDA(ctx, cudaSetDevice(ctx->device));
+    HostTree t;
+    NB_CHECK(fetch_tree(ctx, t));
+    CanonSink s{depth, path_hi, path_lo, kind, body, count, edge, minx, miny, minz, mass, comx, comy, comz};
+    canon_rec(t, 0, 0, 0, 0, t.aabb[6], t.aabb[0], t.aabb[1], t.aabb[2], s);
+    return NB_OK;
+}
+
+int nb_bh_sorted_bodies(nb_ctx *ctx, uint32_t *sorted_bodies) {
+    if (!ctx || !ctx->bh.built || !sorted_bodies) return nb_fail(ctx, NB_ERR_INVALID, "nb_bh_sorted_bodies: no tree");
+    NB_CUDA(ctx, cudaSetDevice(ctx->device));
+    HostTree t;
+    NB_CHECK(fetch_tree(ctx, t));
+    std::vector<uint32_t> order;
+    order.reserve(t.n);
+    CanonSink s{};
+    s.sorted = &order;
+    canon_rec(t, 0, 0, 0, 0, t.aabb[6], t.aabb[0], t.aabb[1], t.aabb[2], s);
+    memcpy(sorted_bodies, order.data(), t.n * sizeof(uint32_t));
+    return NB_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,483 @@
+// Barnes-Hut tree pipeline for sm_100a: AABB -> octant-path keys -> radix sort -> node construction -> centre of mass.
+//
+// Replaces BarnesHutOctree::buildOctree and everything below it (reference
+// src/simulationBackend/BarnesHutTreeAlgorithms/ParallelOctreeTopDownSubtrees.cpp:15-813, BarnesHutOctree.cpp:45-613).
+// The reference inserts bodies one by one under per-node spin locks (one work-group for the top tree, one per
+// subtree) and computes the centre of mass in a single spinning work-group.  None of that is kept.  What IS kept,
+// bit for bit, is the canonical tree those kernels produce:
+//   * AABB seeded with 0.0 (origin always inside), grown to a cube on the two shorter axes;
+//   * a cell with >= 2 bodies is internal and has all 8 children; leaves hold 0 or 1 body;
+//   * octant = 4*(y > mid) + 2*(x > mid) + 1*(z < mid), cell bounds by repeated fp64 `min + edge/2` down the path;
+//   * centre of mass = sum over children in octant order 0..7 of (m*x, m*y, m*z, m).
+//
+// B200-first construction (lock-free, O(N) work, no host round trips):
+//   1. every body descends the cube arithmetically (exactly the reference's fp64 compares) and records its path as
+//      2 x 63-bit keys, 3 bits per level, 42 levels.  The digit is the octant's VISIT RANK 4u+2b+(1-r) in the
+//      reference's traversal order [2,0,3,1,6,4,7,5] (BarnesHutAlgorithm.cpp:370-385), so sorted order == DFS order.
+//   2. stable LSD radix sort of (key_hi, body) (scan_sort.cuh); rare equal-key_hi runs are ordered by key_lo.
+//   3. delta[i] = common-prefix digits of sorted neighbours.  Body i is the FIRST body of the internal cells of depth
+//      delta[i-1]+1 .. delta[i]; an exclusive scan of those counts gives every node its index in a DFS pre-order
+//      array (internal chain of body i, then leaf i).  Empty leaves are implied, never materialised.
+//   4. one thread per body emits its chain + leaf: skip links (first node after the subtree) and parent links by
+//      galloping searches over the sorted keys.
+//   5. centre of mass bottom-up with arrival counters weighted by body count: the last arriving child sums all
+//      children of its parent in octant order (deterministic, bit-identical to the reference's order).
+#include "scan_sort.cuh"
+
+#define NB_NONE 0xffffffffu
+#define NB_FLAG_DEPTH 1u
+#define NB_FLAG_POOL 2u
+
+namespace {
+
+// ---- 1. AABB ----------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+aabb_partial_kernel(const double *__restrict__ x, const double *__restrict__ y, const double *__restrict__ z,
+                    uint64_t n, double *__restrict__ partial /* [6][gridDim.x] */) {
+    // scratch starts at 0.0 like the reference's value-initialised per-work-item arrays (BarnesHutOctree.cpp:58-72)
+    double mnx = 0, mny = 0, mnz = 0, mxx = 0, mxy = 0, mxz = 0;
+    for (uint64_t i = (uint64_t) blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (uint64_t) gridDim.x * blockDim.x) {
+        const double a = x[i], b = y[i], c = z[i];
+        mnx = fmin(mnx, a); mxx = fmax(mxx, a);
+        mny = fmin(mny, b); mxy = fmax(mxy, b);
+        mnz = fmin(mnz, c); mxz = fmax(mxz, c);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        mnx = fmin(mnx, __shfl_xor_sync(0xffffffffu, mnx, o)); mxx = fmax(mxx, __shfl_xor_sync(0xffffffffu, mxx, o));
+        mny = fmin(mny, __shfl_xor_sync(0xffffffffu, mny, o)); mxy = fmax(mxy, __shfl_xor_sync(0xffffffffu, mxy, o));
+        mnz = fmin(mnz, __shfl_xor_sync(0xffffffffu, mnz, o)); mxz = fmax(mxz, __shfl_xor_sync(0xffffffffu, mxz, o));
+    }
+    __shared__ double s[6][8];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (lane == 0) { s[0][warp] = mnx; s[1][warp] = mny; s[2][warp] = mnz; s[3][warp] = mxx; s[4][warp] = mxy; s[5][warp] = mxz; }
+    __syncthreads();
+    if (threadIdx.x < 6) {
+        double v = s[threadIdx.x][0];
+        for (int w = 1; w < 8; ++w) v = threadIdx.x < 3 ? fmin(v, s[threadIdx.x][w]) : fmax(v, s[threadIdx.x][w]);
+        partial[(size_t) threadIdx.x * gridDim.x + blockIdx.x] = v;
+    }
+}
+
+__global__ void __launch_bounds__(256)
+aabb_final_kernel(const double *__restrict__ partial, int n_partials, double *__restrict__ out /* 7 */,
+                  uint32_t *__restrict__ flags) {
+    __shared__ double s[6][256];
+    for (int c = 0; c < 6; ++c) {
+        double v = 0.0;
+        for (int i = threadIdx.x; i < n_partials; i += 256) {
+            const double p = partial[(size_t) c * n_partials + i];
+            v = c < 3 ? fmin(v, p) : fmax(v, p);
+        }
+        s[c][threadIdx.x] = v;
+    }
+    __syncthreads();
+    for (int st = 128; st > 0; st >>= 1) {
+        if ((int) threadIdx.x < st)
+            for (int c = 0; c < 6; ++c)
+                s[c][threadIdx.x] = c < 3 ? fmin(s[c][threadIdx.x], s[c][threadIdx.x + st])
+                                          : fmax(s[c][threadIdx.x], s[c][threadIdx.x + st]);
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) {
+        double min_x = s[0][0], min_y = s[1][0], min_z = s[2][0], max_x = s[3][0], max_y = s[4][0], max_z = s[5][0];
+        // cube growth, BarnesHutOctree.cpp:162-190 (same operations, same tie order x, y, z)
+        const double x_length = fabs(__dsub_rn(max_x, min_x));
+        const double y_length = fabs(__dsub_rn(max_y, min_y));
+        const double z_length = fabs(__dsub_rn(max_z, min_z));
+        const double maxEdgeLength = fmax(x_length, fmax(y_length, z_length));
+        const double gx = __ddiv_rn(__dsub_rn(maxEdgeLength, x_length), 2.0);
+        const double gy = __ddiv_rn(__dsub_rn(maxEdgeLength, y_length), 2.0);
+        const double gz = __ddiv_rn(__dsub_rn(maxEdgeLength, z_length), 2.0);
+        if (maxEdgeLength == x_length) {
+            min_z = __dsub_rn(min_z, gz); min_y = __dsub_rn(min_y, gy);
+            max_z = __dadd_rn(max_z, gz); max_y = __dadd_rn(max_y, gy);
+        } else if (maxEdgeLength == y_length) {
+            min_x = __dsub_rn(min_x, gx); min_z = __dsub_rn(min_z, gz);
+            max_x = __dadd_rn(max_x, gx); max_z = __dadd_rn(max_z, gz);
+        } else {
+            min_x = __dsub_rn(min_x, gx); min_y = __dsub_rn(min_y, gy);
+            max_x = __dadd_rn(max_x, gx); max_y = __dadd_rn(max_y, gy);
+        }
+        out[0] = min_x; out[1] = min_y; out[2] = min_z;
+        out[3] = max_x; out[4] = max_y; out[5] = max_z;
+        out[6] = maxEdgeLength;
+        flags[0] = 0; flags[1] = 0; flags[2] = 0; flags[3] = 0;
+    }
+}
+
+// ---- 2. octant-path keys --------------------------------------------------------------------------------------------
+// Descent test of ParallelOctreeTopDownSubtrees.cpp:400-406 with the child bounds of :256-315.
+__global__ void __launch_bounds__(256)
+keys_kernel(const double *__restrict__ x, const double *__restrict__ y, const double *__restrict__ z, uint64_t n,
+            const double *__restrict__ aabb, uint64_t *__restrict__ key_hi, uint64_t *__restrict__ key_lo) {
+    const uint64_t i = (uint64_t) blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const double px = x[i], py = y[i], pz = z[i];
+    double mnx = aabb[0], mny = aabb[1], mnz = aabb[2], edge = aabb[6];
+    uint64_t hi = 0, lo = 0;
+#pragma unroll 1
+    for (int half = 0; half < 2; ++half) {
+        uint64_t k = 0;
+#pragma unroll
+        for (int l = 0; l < 21; ++l) {
+            const double h = __dmul_rn(edge, 0.5);           // parentEdgeLength / 2 (exact halving)
+            const double midx = __dadd_rn(mnx, h);
+            const double midy = __dadd_rn(mny, h);
+            const double midz = __dadd_rn(mnz, h);
+            const bool upper = py > midy;
+            const bool right = px > midx;
+            const bool back = pz < midz;
+            // visit-rank digit: 4u + 2b + (1-r)
+            const uint64_t digit = (upper ? 4u : 0u) | (back ? 2u : 0u) | (right ? 0u : 1u);
+            k = (k << 3) | digit;
+            mny = upper ? midy : mny;
+            mnx = right ? midx : mnx;
+            mnz = back ? mnz : midz;                         // z gets +h when back == 0 (:256-315)
+            edge = h;
+        }
+        if (half == 0) hi = k; else lo = k;
+    }
+    key_hi[i] = hi;
+    key_lo[i] = lo;
+}
+
+// ---- 2b. order equal-key_hi runs by key_lo (bodies closer than edge * 2^-21) -----------------------------------------
+__global__ void __launch_bounds__(256)
+fix_ties_kernel(const uint64_t *__restrict__ hi_sorted, const uint64_t *__restrict__ key_lo, uint32_t *__restrict__ perm,
+                uint64_t n, uint32_t *__restrict__ flags) {
+    const uint64_t i = (uint64_t) blockIdx.x * blockDim.x + threadIdx.x;
+    if (i + 1 >= n) return;
+    const uint64_t k = hi_sorted[i];
+    if (hi_sorted[i + 1] != k) return;
+    if (i > 0 && hi_sorted[i - 1] == k) return;
+    uint64_t e = i + 1;
+    while (e + 1 < n && hi_sorted[e + 1] == k) ++e;
+    for (uint64_t a = i + 1; a <= e; ++a) {  // insertion sort of the run by key_lo
+        const uint32_t pa = perm[a];
+        const uint64_t la = key_lo[pa];
+        uint64_t b = a;
+        while (b > i) {
+            const uint32_t pb = perm[b - 1];
+            const uint64_t lb = key_lo[pb];
+            if (lb == la) atomicOr(&flags[0], NB_FLAG_DEPTH);  // identical 42-level paths: coincident bodies
+            if (lb <= la) break;
+            perm[b] = pb;
+            --b;
+        }
+        perm[b] = pa;
+    }
+}
+
+// ---- 3. gather into sorted order ---------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+gather_kernel(const uint32_t *__restrict__ perm, uint64_t n, const double *__restrict__ x, const double *__restrict__ y,
+              const double *__restrict__ z, const double *__restrict__ m, const uint64_t *__restrict__ key_lo,
+              double *__restrict__ sx, double *__restrict__ sy, double *__restrict__ sz, double *__restrict__ sm,
+              uint64_t *__restrict__ lo_sorted) {
+    const uint64_t i = (uint64_t) blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const uint32_t b = perm[i];
+    sx[i] = x[b]; sy[i] = y[b]; sz[i] = z[b]; sm[i] = m[b];
+    lo_sorted[i] = key_lo[b];
+}
+
+__device__ __forceinline__ int common_digits(uint64_t hi_a, uint64_t lo_a, uint64_t hi_b, uint64_t lo_b) {
+    const uint64_t xh = hi_a ^ hi_b;
+    if (xh) return (__clzll((long long) xh) - 1) / 3;
+    const uint64_t xl = lo_a ^ lo_b;
+    if (xl) return 21 + (__clzll((long long) xl) - 1) / 3;
+    return NB_MAX_TREE_DEPTH;
+}
+
+// do keys a and b share their first d digits?
+__device__ __forceinline__ bool share_prefix(uint64_t hi_a, uint64_t lo_a, uint64_t hi_b, uint64_t lo_b, int d) {
+    if (d <= 21) return ((hi_a ^ hi_b) >> (63 - 3 * d)) == 0;
+    return hi_a == hi_b && ((lo_a ^ lo_b) >> (63 - 3 * (d - 21))) == 0;
+}
+
+__device__ __forceinline__ uint32_t digit_at(uint64_t hi, uint64_t lo, int level) {
+    return level < 21 ? (uint32_t) ((hi >> (60 - 3 * level)) & 7) : (uint32_t) ((lo >> (60 - 3 * (level - 21))) & 7);
+}
+
+// ---- 3b. neighbour prefix lengths and per-body internal-node counts -----------------------------------------------------
+__global__ void __launch_bounds__(256)
+delta_kernel(const uint64_t *__restrict__ hi, const uint64_t *__restrict__ lo, uint64_t n, int32_t *__restrict__ delta,
+             uint32_t *__restrict__ cnt, uint32_t *__restrict__ flags) {
+    const uint64_t i = (uint64_t) blockIdx.x * blockDim.x + threadIdx.x;
+    int d_cur = -1;
+    if (i < n) {
+        const uint64_t h = hi[i], l = lo[i];
+        const int d_prev = i > 0 ? common_digits(hi[i - 1], lo[i - 1], h, l) : -1;
+        d_cur = i + 1 < n ? common_digits(h, l, hi[i + 1], lo[i + 1]) : -1;
+        delta[i] = d_cur;
+        cnt[i] = d_cur > d_prev ? (uint32_t) (d_cur - d_prev) : 0u;
+        if (d_cur >= NB_MAX_TREE_DEPTH) atomicOr(&flags[0], NB_FLAG_DEPTH);
+    }
+    // max depth of the tree = deepest leaf = max(delta) + 1
+    int mx = d_cur;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) mx = max(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+    if ((threadIdx.x & 31) == 0 && mx >= 0) atomicMax(&flags[2], (uint32_t) (mx + 1));
+}
+
+// ---- 4. node emission ---------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128)
+emit_kernel(const uint64_t *__restrict__ hi, const uint64_t *__restrict__ lo, const int32_t *__restrict__ delta,
+            const uint32_t *__restrict__ base, uint64_t n, uint64_t cap_nodes, uint32_t *__restrict__ flags,
+            uint2 *__restrict__ meta, uint32_t *__restrict__ parent, uint32_t *__restrict__ first_body,
+            uint32_t *__restrict__ body_count, uint32_t *__restrict__ arrive, uint32_t *__restrict__ leaf_node) {
+    const uint64_t i = (uint64_t) blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const uint64_t total_internal = flags[1];
+    const uint64_t M = n + total_internal;
+    if (M > cap_nodes) {  // reference: silent overflow of the 16N pool (README.md:117-118); here: reported
+        if (i == 0) atomicOr(&flags[0], NB_FLAG_POOL);
+        return;
+    }
+    const uint64_t hi_i = hi[i], lo_i = lo[i];
+    const int d_prev = i > 0 ? delta[i - 1] : -1;
+    const int d_cur = delta[i];
+    const uint32_t c = d_cur > d_prev ? (uint32_t) (d_cur - d_prev) : 0u;
+    const uint64_t b = base[i];
+    const uint64_t head = i + b;          // first node that starts at body i
+    const uint64_t leaf = head + c;
+
+    // parent of the head: the depth-d_prev cell that contains bodies i-1 and i; its first body by galloping left
+    uint32_t head_parent = NB_NONE;
+    if (i > 0) {
+        uint64_t f = i - 1;  // shares d_prev digits with i by definition
+        uint64_t step = 1;
+        while (f >= step && share_prefix(hi[f - step], lo[f - step], hi_i, lo_i, d_prev)) { f -= step; step <<= 1; }
+        while (step > 1) {
+            step >>= 1;
+            if (f >= step && share_prefix(hi[f - step], lo[f - step], hi_i, lo_i, d_prev)) f -= step;
+        }
+        const int d_before_f = f > 0 ? delta[f - 1] : -1;
+        head_parent = (uint32_t) (f + base[f] + (uint64_t) (d_prev - d_before_f - 1));
+    }
+
+    // chain of internal nodes first-bodied by i, deepest first so the right boundary only moves outwards
+    uint64_t r = i + 1;  // i+1 shares d_cur digits when c > 0
+    for (int k = (int) c - 1; k >= 0; --k) {
+        const int d = d_prev + 1 + k;
+        uint64_t step = 1;
+        while (r + step < n && share_prefix(hi[r + step], lo[r + step], hi_i, lo_i, d)) { r += step; step <<= 1; }
+        while (step > 1) {
+            step >>= 1;
+            if (r + step < n && share_prefix(hi[r + step], lo[r + step], hi_i, lo_i, d)) r += step;
+        }
+        const uint64_t node = head + k;
+        const uint64_t skip = r + 1 < n ? (r + 1) + base[r + 1] : M;
+        meta[node] = make_uint2((uint32_t) skip, (uint32_t) d);
+        first_body[node] = (uint32_t) i;
+        body_count[node] = (uint32_t) (r - i + 1);
+        arrive[node] = 0;
+        parent[node] = k > 0 ? (uint32_t) (node - 1) : head_parent;
+    }
+    meta[leaf] = make_uint2((uint32_t) (leaf + 1), NB_LEAF_FLAG | (uint32_t) i);
+    first_body[leaf] = (uint32_t) i;
+    body_count[leaf] = 1;
+    parent[leaf] = c > 0 ? (uint32_t) (leaf - 1) : head_parent;
+    leaf_node[i] = (uint32_t) leaf;
+}
+
+// ---- 5. centre of mass ------------------------------------------------------------------------------------------------------
+// leaf: prepareCenterOfMass (BarnesHutOctree.cpp:216-226); internal: the octant-ordered sum of :299-317.
+__global__ void __launch_bounds__(128)
+com_kernel(uint64_t n, const uint32_t *__restrict__ flags_in, const double *__restrict__ sx, const double *__restrict__ sy,
+           const double *__restrict__ sz, const double *__restrict__ sm, const uint64_t *__restrict__ hi,
+           const uint64_t *__restrict__ lo, const uint32_t *__restrict__ leaf_node, const uint2 *meta,
+           const uint32_t *__restrict__ parent, const uint32_t *__restrict__ first_body,
+           const uint32_t *__restrict__ body_count, uint32_t *arrive, double *com, double *msum) {
+    const uint64_t i = (uint64_t) blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    if (flags_in[0] & NB_FLAG_POOL) return;
+    uint32_t cur = leaf_node[i];
+    {
+        const double m = sm[i], px = sx[i], py = sy[i], pz = sz[i];
+        double *c4 = com + 4 * (size_t) cur;
+        double *s3 = msum + 3 * (size_t) cur;
+        s3[0] = __dmul_rn(px, m); s3[1] = __dmul_rn(py, m); s3[2] = __dmul_rn(pz, m);
+        // the reference's traversal divides the stored sum by the mass (BarnesHutAlgorithm.cpp:351-353), also for
+        // body leaves: (x*m)/m, which is not always x.  Store that quotient once instead of dividing per visit.
+        c4[0] = __ddiv_rn(s3[0], m); c4[1] = __ddiv_rn(s3[1], m); c4[2] = __ddiv_rn(s3[2], m); c4[3] = m;
+    }
+    uint32_t my_count = 1;
+    while (true) {
+        const uint32_t p = parent[cur];
+        if (p == NB_NONE) break;
+        __threadfence();
+        const uint32_t total = body_count[p];
+        const uint32_t old = atomicAdd(&arrive[p], my_count);
+        if (old + my_count != total) break;
+        __threadfence();
+        // last arrival: every child of p is final.  Collect them by visit rank, then sum in octant order.
+        const uint2 mp = meta[p];
+        const int depth = (int) mp.y;
+        double vx[8], vy[8], vz[8], vm[8];
+#pragma unroll
+        for (int r = 0; r < 8; ++r) { vx[r] = 0; vy[r] = 0; vz[r] = 0; vm[r] = 0; }
+        uint32_t ch = p + 1;
+        while (ch < mp.x) {
+            const uint2 mc = __ldcg(&meta[ch]);
+            const uint32_t fb = (mc.y & NB_LEAF_FLAG) ? (mc.y & ~NB_LEAF_FLAG) : first_body[ch];
+            const uint32_t rank = digit_at(hi[fb], lo[fb], depth);
+            const double cm = __ldcg(com + 4 * (size_t) ch + 3);
+            const double cx = __ldcg(msum + 3 * (size_t) ch + 0);
+            const double cy = __ldcg(msum + 3 * (size_t) ch + 1);
+            const double cz = __ldcg(msum + 3 * (size_t) ch + 2);
+#pragma unroll
+            for (int r = 0; r < 8; ++r)
+                if (rank == (uint32_t) r) { vx[r] = cx; vy[r] = cy; vz[r] = cz; vm[r] = cm; }
+            ch = mc.x;
+        }
+        // octant code o = 4u + 2r + b  <->  visit rank 4u + 2b + (1-r):  octants 0..7 are ranks 1,3,0,2,5,7,4,6
+        const int rank_of_octant[8] = {1, 3, 0, 2, 5, 7, 4, 6};
+        double sumMasses = 0, cx = 0, cy = 0, cz = 0;
+#pragma unroll
+        for (int o = 0; o < 8; ++o) {
+            const int r = rank_of_octant[o];
+            cx = __dadd_rn(cx, vx[r]);
+            cy = __dadd_rn(cy, vy[r]);
+            cz = __dadd_rn(cz, vz[r]);
+            sumMasses = __dadd_rn(sumMasses, vm[r]);
+        }
+        double *s3 = msum + 3 * (size_t) p;
+        s3[0] = cx; s3[1] = cy; s3[2] = cz;
+        double *c4 = com + 4 * (size_t) p;
+        c4[0] = __ddiv_rn(cx, sumMasses); c4[1] = __ddiv_rn(cy, sumMasses); c4[2] = __ddiv_rn(cz, sumMasses);
+        c4[3] = sumMasses;
+        my_count = total;
+        cur = p;
+    }
+}
+
+
+}  // namespace
+
+// -----------------------------------------------------------------------------------------------------------------------------
+int nbk_bh_reserve(nb_ctx *ctx) {
+    nb_bh_state &b = ctx->bh;
+    const uint64_t n = ctx->n;
+    // node pool: the reference holds storage_size_param*N canonical nodes (1 + 8 per internal node); the same budget
+    // in internal nodes is param*N/8 (2N for the default 16).
+    uint64_t param = ctx->cfg.storage_size_param > 0 ? (uint64_t) ctx->cfg.storage_size_param : 16;
+    const uint64_t cap_nodes = n + (param * n + 7) / 8 + 8;
+    if (n <= b.cap_bodies && cap_nodes <= b.cap_nodes) return NB_OK;
+    nbk_bh_release(ctx);
+    const uint64_t nb = n + 32;
+    NB_CHECK(nb_alloc(ctx, &b.key_hi, nb));
+    NB_CHECK(nb_alloc(ctx, &b.key_lo, nb));
+    NB_CHECK(nb_alloc(ctx, &b.key_hi_alt, nb));
+    NB_CHECK(nb_alloc(ctx, &b.perm, nb));
+    NB_CHECK(nb_alloc(ctx, &b.perm_alt, nb));
+    NB_CHECK(nb_alloc(ctx, &b.sx, nb));
+    NB_CHECK(nb_alloc(ctx, &b.sy, nb));
+    NB_CHECK(nb_alloc(ctx, &b.sz, nb));
+    NB_CHECK(nb_alloc(ctx, &b.sm, nb));
+    NB_CHECK(nb_alloc(ctx, &b.delta, nb));
+    NB_CHECK(nb_alloc(ctx, &b.chain_cnt, nb));
+    NB_CHECK(nb_alloc(ctx, &b.chain_base, nb));
+    NB_CHECK(nb_alloc(ctx, &b.leaf_node, nb));
+    NB_CHECK(nb_alloc(ctx, &b.asx, nb));
+    NB_CHECK(nb_alloc(ctx, &b.asy, nb));
+    NB_CHECK(nb_alloc(ctx, &b.asz, nb));
+    NB_CHECK(nb_alloc(ctx, &b.visits, nb));
+    NB_CHECK(nb_alloc(ctx, &b.com, 4 * cap_nodes));
+    NB_CHECK(nb_alloc(ctx, &b.msum, 3 * cap_nodes));
+    NB_CHECK(nb_alloc(ctx, &b.meta, cap_nodes));
+    NB_CHECK(nb_alloc(ctx, &b.parent, cap_nodes));
+    NB_CHECK(nb_alloc(ctx, &b.first_body, cap_nodes));
+    NB_CHECK(nb_alloc(ctx, &b.body_count, cap_nodes));
+    NB_CHECK(nb_alloc(ctx, &b.arrive, cap_nodes));
+    const size_t scratch = nbprim::rs_scratch_elems(nb) + nbprim::scan_tiles_for(nb) + 64;
+    NB_CHECK(nb_alloc(ctx, &b.hist, scratch));
+    NB_CHECK(nb_alloc(ctx, &b.aabb_dev, 8));
+    NB_CHECK(nb_alloc(ctx, &b.aabb_partial, 6 * 1024));
+    NB_CHECK(nb_alloc(ctx, &b.dev_flags, 8));
+    NB_CHECK(nb_alloc(ctx, &b.stat_totals, 4));
+    NB_CUDA(ctx, cudaMemsetAsync(b.dev_flags, 0, 8 * sizeof(uint32_t), ctx->stream));
+    b.cap_bodies = n;
+    b.cap_nodes = cap_nodes;
+    b.built = false;
+    return NB_OK;
+}
+
+void nbk_bh_release(nb_ctx *ctx) {
+    nb_bh_state &b = ctx->bh;
+    nb_free(&b.key_hi); nb_free(&b.key_lo); nb_free(&b.key_hi_alt); nb_free(&b.perm); nb_free(&b.perm_alt);
+    nb_free(&b.sx); nb_free(&b.sy); nb_free(&b.sz); nb_free(&b.sm); nb_free(&b.delta); nb_free(&b.chain_cnt);
+    nb_free(&b.chain_base); nb_free(&b.leaf_node); nb_free(&b.asx); nb_free(&b.asy); nb_free(&b.asz);
+    nb_free(&b.visits); nb_free(&b.com); nb_free(&b.msum); nb_free(&b.meta); nb_free(&b.parent);
+    nb_free(&b.first_body); nb_free(&b.body_count); nb_free(&b.arrive); nb_free(&b.hist); nb_free(&b.aabb_dev);
+    nb_free(&b.aabb_partial); nb_free(&b.dev_flags); nb_free(&b.stat_totals);
+    b.cap_bodies = b.cap_nodes = 0;
+    b.built = false;
+}
+
+int nbk_bh_aabb(nb_ctx *ctx) {
+    nb_bh_state &b = ctx->bh;
+    const uint64_t n = ctx->n;
+    int blocks = (int) ((n + 255) / 256);
+    if (blocks > 1024) blocks = 1024;
+    if (blocks < 1) blocks = 1;
+    aabb_partial_kernel<<<blocks, 256, 0, ctx->stream>>>(ctx->x, ctx->y, ctx->z, n, b.aabb_partial);
+    NB_LAUNCH_CHECK(ctx);
+    aabb_final_kernel<<<1, 256, 0, ctx->stream>>>(b.aabb_partial, blocks, b.aabb_dev, b.dev_flags);
+    NB_LAUNCH_CHECK(ctx);
+    return NB_OK;
+}
+
+int nbk_bh_build(nb_ctx *ctx) {
+    nb_bh_state &b = ctx->bh;
+    const uint64_t n = ctx->n;
+    if (n == 0) return nb_fail(ctx, NB_ERR_INVALID, "nb_bh_build: no bodies");
+    if (n >= 0x7fffffffull) return nb_fail(ctx, NB_ERR_UNSUPPORTED, "nb_bh_build: N must be < 2^31");
+    NB_CHECK(nbk_bh_reserve(ctx));
+    const unsigned g256 = (unsigned) ((n + 255) / 256), g128 = (unsigned) ((n + 127) / 128);
+    nb_timer_scope total(ctx, NB_T_TREE_TOTAL);
+    {
+        nb_timer_scope t(ctx, NB_T_AABB);
+        NB_CHECK(nbk_bh_aabb(ctx));
+    }
+    uint64_t *hi_sorted = nullptr;
+    uint32_t *perm_sorted = nullptr;
+    {
+        nb_timer_scope t(ctx, NB_T_KEYS_SORT);
+        keys_kernel<<<g256, 256, 0, ctx->stream>>>(ctx->x, ctx->y, ctx->z, n, b.aabb_dev, b.key_hi, b.key_lo);
+        NB_LAUNCH_CHECK(ctx);
+        NB_CHECK(nbprim::radix_sort_pairs(ctx, b.key_hi, b.perm, b.key_hi_alt, b.perm_alt, n, 63, b.hist, &hi_sorted,
+                                          &perm_sorted, true));
+        fix_ties_kernel<<<g256, 256, 0, ctx->stream>>>(hi_sorted, b.key_lo, perm_sorted, n, b.dev_flags);
+        NB_LAUNCH_CHECK(ctx);
+        // key_hi_alt / perm_alt are reused below: make the sorted data live in (key_hi, perm)
+        if (hi_sorted != b.key_hi) {
+            uint64_t *tk = b.key_hi; b.key_hi = b.key_hi_alt; b.key_hi_alt = tk;
+            uint32_t *tp = b.perm; b.perm = b.perm_alt; b.perm_alt = tp;
+        }
+        // sorted positions / masses / key_lo (key_hi_alt receives the sorted key_lo)
+        gather_kernel<<<g256, 256, 0, ctx->stream>>>(b.perm, n, ctx->x, ctx->y, ctx->z, ctx->m, b.key_lo, b.sx, b.sy,
+                                                     b.sz, b.sm, b.key_hi_alt);
+        NB_LAUNCH_CHECK(ctx);
+    }
+    const uint64_t *hi = b.key_hi, *lo = b.key_hi_alt;
+    {
+        nb_timer_scope t(ctx, NB_T_BUILD);
+        delta_kernel<<<g256, 256, 0, ctx->stream>>>(hi, lo, n, b.delta, b.chain_cnt, b.dev_flags);
+        NB_LAUNCH_CHECK(ctx);
+        uint32_t *tile_tmp = b.hist;  // scan scratch (sort is finished)
+        NB_CHECK(nbprim::exclusive_scan_u32(ctx, b.chain_cnt, b.chain_base, n, tile_tmp, b.dev_flags + 1));
+        emit_kernel<<<g128, 128, 0, ctx->stream>>>(hi, lo, b.delta, b.chain_base, n, b.cap_nodes, b.dev_flags, b.meta,
+                                                   b.parent, b.first_body, b.body_count, b.arrive, b.leaf_node);
+        NB_LAUNCH_CHECK(ctx);
+    }
+    {
+        nb_timer_scope t(ctx, NB_T_COM);
+        com_kernel<<<g128, 128, 0, ctx->stream>>>(n, b.dev_flags, b.sx, b.sy, b.sz, b.sm, hi, lo, b.leaf_node, b.meta,
+                                                  b.parent, b.first_body, b.body_count, b.arrive, b.com, b.msum);
+        NB_LAUNCH_CHECK(ctx);
+    }
+    b.built = true;
+    return NB_OK;
+}

@@ -1,0 +1,168 @@
+// Shared definitions of the sm_100a gravity kernels: context, error handling, small device helpers.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string>
+#include <vector>
+
+#include "../../include/nbody_b200.h"
+
+#define NB_SM_COUNT_FALLBACK 148
+
+// Packed source record of the all-pairs kernel: one 48-byte AoS entry per source body so a whole tile is a
+// single contiguous TMA bulk copy.  c1 = 1.5*m and c2 = 1.875*m are the Taylor coefficients of
+// m*(1-e)^(-3/2) (see naive.cu).
+struct __align__(16) nb_src_rec {
+    double x, y, z, m;
+    double c1, c2;
+};
+
+// Barnes-Hut node record (DFS pre-order array, children of a node in the reference's visit order
+// [2,0,3,1,6,4,7,5], BarnesHutAlgorithm.cpp:370-385).  40 bytes of traversal payload per node:
+//   com[4*n+0..2] = centre of mass (already divided by the mass), com[4*n+3] = mass     (32 B)
+//   meta[n].x     = index of the first node AFTER this node's subtree ("skip link")
+//   meta[n].y     = body leaf: 0x80000000 | sorted index of the body;  internal node: depth        ( 8 B)
+#define NB_LEAF_FLAG 0x80000000u
+
+struct nb_bh_state {
+    // per-body, sorted order
+    uint64_t *key_hi = nullptr, *key_lo = nullptr;          // octant-path keys (visit-rank digits)
+    uint64_t *key_hi_alt = nullptr;                          // radix sort ping-pong
+    uint32_t *perm = nullptr, *perm_alt = nullptr;           // sorted index -> body id
+    double *sx = nullptr, *sy = nullptr, *sz = nullptr, *sm = nullptr;  // positions / masses gathered into sorted order
+    int32_t *delta = nullptr;                                // common-prefix digits of sorted neighbours (i, i+1)
+    uint32_t *chain_cnt = nullptr, *chain_base = nullptr;    // internal nodes starting at body i, and their scan
+    uint32_t *leaf_node = nullptr;                           // node index of the leaf of sorted body i
+    // per-node
+    double *com = nullptr;                                   // 4 doubles per node
+    double *msum = nullptr;                                  // 3 doubles per node: mass-weighted sums (reference's massCenters_*)
+    uint2 *meta = nullptr;
+    uint32_t *parent = nullptr;
+    uint32_t *first_body = nullptr;                          // sorted index of the first body in the node's cell
+    uint32_t *body_count = nullptr;
+    uint32_t *arrive = nullptr;                              // COM pass arrival counters
+    uint8_t *nchild = nullptr;
+    // sort scratch
+    uint32_t *hist = nullptr;
+    void *scan_tmp = nullptr;
+    size_t scan_tmp_bytes = 0;
+    // results
+    double *asx = nullptr, *asy = nullptr, *asz = nullptr;   // accelerations in sorted order
+    uint32_t *visits = nullptr;                              // per-body visit counters (stats)
+    unsigned long long *stat_totals = nullptr;               // {visits, accepts}
+    // device scalars
+    double *aabb_dev = nullptr;                              // 7 doubles: min xyz, max xyz, edge
+    double *aabb_partial = nullptr;
+    uint32_t *dev_flags = nullptr;                           // [0]=depth overflow flag, [1]=num nodes, [2]=max depth
+    uint64_t cap_bodies = 0, cap_nodes = 0;
+    uint64_t num_nodes = 0, num_internal = 0;
+    uint32_t max_depth = 0;
+    double aabb[7] = {0, 0, 0, 0, 0, 0, 0};
+    bool built = false;
+    bool stats_enabled = false;
+};
+
+struct nb_ctx {
+    nb_config cfg;
+    int device = 0;
+    int sm_count = NB_SM_COUNT_FALLBACK;
+    cudaStream_t stream = nullptr;
+    std::string last_error;
+    std::string device_name;
+    uint64_t n = 0, cap = 0;
+    // SoA state (body-id order)
+    double *m = nullptr, *x = nullptr, *y = nullptr, *z = nullptr;
+    double *vx = nullptr, *vy = nullptr, *vz = nullptr;
+    double *ax = nullptr, *ay = nullptr, *az = nullptr;
+    double *anorm = nullptr;
+    // naive
+    nb_src_rec *src = nullptr;
+    uint64_t src_cap = 0;
+    // energy
+    double *e_partial = nullptr;  // 2*n doubles: kinetic, potential per body
+    // host staging (pinned)
+    double *h_pinned = nullptr;
+    size_t h_pinned_bytes = 0;
+    nb_bh_state bh;
+    // timers
+    bool timers_enabled = false;
+    cudaEvent_t ev[2 * NB_T_COUNT] = {};
+    bool ev_valid[NB_T_COUNT] = {};
+    uint64_t launches = 0;
+    // comm
+    void *nccl_comm = nullptr;
+    int world = 1, rank = 0;
+};
+
+int nb_fail(nb_ctx *ctx, int status, const char *fmt, ...);
+
+#define NB_CUDA(ctx, expr)                                                                              \
+    do {                                                                                                \
+        cudaError_t _e = (expr);                                                                        \
+        if (_e != cudaSuccess)                                                                          \
+            return nb_fail((ctx), NB_ERR_CUDA, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e),  \
+                           __FILE__, __LINE__);                                                         \
+    } while (0)
+
+#define NB_CHECK(expr)                \
+    do {                              \
+        int _s = (expr);              \
+        if (_s != NB_OK) return _s;   \
+    } while (0)
+
+#define NB_LAUNCH_CHECK(ctx)                                                                            \
+    do {                                                                                                \
+        (ctx)->launches++;                                                                              \
+        cudaError_t _e = cudaGetLastError();                                                            \
+        if (_e != cudaSuccess)                                                                          \
+            return nb_fail((ctx), NB_ERR_CUDA, "kernel launch failed: %s (%s:%d)", cudaGetErrorString(_e), \
+                           __FILE__, __LINE__);                                                         \
+    } while (0)
+
+template <typename T>
+static inline int nb_alloc(nb_ctx *ctx, T **p, size_t count) {
+    if (*p) { cudaFree(*p); *p = nullptr; }
+    if (count == 0) return NB_OK;
+    NB_CUDA(ctx, cudaMalloc((void **) p, count * sizeof(T)));
+    return NB_OK;
+}
+template <typename T>
+static inline void nb_free(T **p) {
+    if (*p) { cudaFree(*p); *p = nullptr; }
+}
+
+struct nb_timer_scope {
+    nb_ctx *ctx; int id;
+    nb_timer_scope(nb_ctx *c, int i) : ctx(c), id(i) {
+        if (ctx->timers_enabled) cudaEventRecord(ctx->ev[2 * id], ctx->stream);
+    }
+    ~nb_timer_scope() {
+        if (ctx->timers_enabled) { cudaEventRecord(ctx->ev[2 * id + 1], ctx->stream); ctx->ev_valid[id] = true; }
+    }
+};
+
+// ---- internal entry points implemented across the .cu files ------------------------------------------------
+int nbk_naive_accel(nb_ctx *ctx, uint64_t i_begin, uint64_t i_end);
+int nbk_leapfrog_part1(nb_ctx *ctx, double dt);
+int nbk_leapfrog_part2(nb_ctx *ctx, double dt);
+int nbk_leapfrog_part2_part1(nb_ctx *ctx, double dt);
+int nbk_accel_norm(nb_ctx *ctx);
+int nbk_energy(nb_ctx *ctx, uint64_t j_begin, uint64_t j_end);
+int nbk_fp64_peak(nb_ctx *ctx, double *tflops);
+int nbk_bh_reserve(nb_ctx *ctx);
+void nbk_bh_release(nb_ctx *ctx);
+int nbk_bh_aabb(nb_ctx *ctx);
+int nbk_bh_build(nb_ctx *ctx);
+int nbk_bh_accel(nb_ctx *ctx, uint64_t s_begin, uint64_t s_end);
+int nbk_bh_scatter_accel(nb_ctx *ctx);
+int nbk_comm_allgather_accel(nb_ctx *ctx, double *ax, double *ay, double *az, uint64_t n);
+void nbk_comm_destroy(nb_ctx *ctx);
+int nbk_comm_allreduce_sum(nb_ctx *ctx, double *buf, size_t count);
+
+// ---- device helpers ------------------------------------------------------------------------------------------
+__device__ __forceinline__ double nb_rsqrt_seed(double x) {
+    double y;
+    asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));  // MUFU.RSQ64H, ~2^-21 relative
+    return y;
+}

@@ -1,0 +1,258 @@
+// All-pairs fp64 gravity for sm_100a.
+//
+// Replaces NaiveAlgorithm::computeAccelerations_opt_{0,1,2} (reference src/simulationBackend/NaiveAlgorithm.cpp:262-482):
+//     a_i = G * sum_{j=0..N-1} m_j * r_ij * (|r_ij|^2 + eps2)^(-3/2),   r_ij = x_j - x_i,  j ascending, self term included.
+//
+// Design (B200-first, not a translation of the SYCL tiles):
+//   * sources are pre-packed into 48-byte AoS records {x,y,z,m,1.5m,1.875m}; a tile of `tile_len` records is ONE
+//     contiguous TMA bulk copy (cp.async.bulk, SASS UBLKCP) into shared memory, completion tracked by mbarriers;
+//   * warp specialisation: 4 consumer warps + 1 producer warp per CTA, NB_NAIVE_STAGES-deep full/empty mbarrier ring,
+//     no __syncthreads in the steady state;
+//   * register blocking: each consumer thread owns IPT target bodies, so one broadcast LDS.128 triple feeds
+//     IPT*32 interactions;
+//   * the FP64 pipe is the roofline.  Per interaction: 3 DADD (r), 3 DFMA (d2 = r.r + eps2), MUFU.RSQ64H seed
+//     y0 ~ d2^(-1/2) (XU pipe, not DP), then   y2 = y0*y0;  e = 1 - d2*y2;  y3 = y2*y0;
+//     s = m*d2^(-3/2) = y3 * (m + e*(1.5m + 1.875m*e))   [Taylor of (1-e)^(-3/2), |e| <~ 2^-20 -> error ~2e-18]
+//     = 6 DP ops including the mass multiply, then 3 DFMA accumulate: 15 DP instructions for the 21 algorithmic flops
+//     (SURVEY 8d).  precise_rsqrt=0 drops the quadratic term (14 DP ops, ~2e-12 relative).
+//   * summation order per target is j ascending exactly as the reference; the only differences to the oracle are the
+//     rsqrt refinement and FMA contraction (~1e-16 relative per term).
+#include "common.cuh"
+
+#define NB_NAIVE_CONSUMER_WARPS 4
+#define NB_NAIVE_THREADS (32 * (NB_NAIVE_CONSUMER_WARPS + 1))
+#define NB_NAIVE_STAGES 4
+
+namespace {
+
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t) __cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
+    uint32_t done;
+    do {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(done)
+            : "r"(smem_u32(bar)), "r"(parity)
+            : "memory");
+    } while (!done);
+}
+__device__ __forceinline__ void bulk_g2s(void *dst, const void *src, uint32_t bytes, uint64_t *bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                     smem_u32(dst)),
+                 "l"(src), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+
+__global__ void pack_sources_kernel(const double *__restrict__ m, const double *__restrict__ x,
+                                    const double *__restrict__ y, const double *__restrict__ z,
+                                    nb_src_rec *__restrict__ out, uint64_t n, uint64_t n_pad) {
+    uint64_t i = (uint64_t) blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_pad) return;
+    nb_src_rec r;
+    if (i < n) {
+        double mm = m[i];
+        r.x = x[i]; r.y = y[i]; r.z = z[i]; r.m = mm;
+        r.c1 = 1.5 * mm; r.c2 = 1.875 * mm;
+    } else {  // padding: zero mass => contributes exactly 0 (eps2 > 0 keeps d2 finite and positive)
+        r.x = r.y = r.z = r.m = r.c1 = r.c2 = 0.0;
+    }
+    out[i] = r;
+}
+
+template <int IPT, bool PRECISE>
+__global__ void __launch_bounds__(NB_NAIVE_THREADS, 2)
+naive_accel_kernel(const nb_src_rec *__restrict__ src, uint32_t n_tiles, uint32_t tile_len,
+                   const double *__restrict__ x, const double *__restrict__ y, const double *__restrict__ z,
+                   uint64_t i_begin, uint64_t i_end, double eps2, double G, double *__restrict__ ax,
+                   double *__restrict__ ay, double *__restrict__ az) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    uint64_t *full = reinterpret_cast<uint64_t *>(smem_raw);
+    uint64_t *empty = full + NB_NAIVE_STAGES;
+    nb_src_rec *tiles = reinterpret_cast<nb_src_rec *>(smem_raw + 128);
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+    const uint32_t tile_bytes = tile_len * (uint32_t) sizeof(nb_src_rec);
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < NB_NAIVE_STAGES; ++s) {
+            mbar_init(&full[s], 1);
+            mbar_init(&empty[s], NB_NAIVE_CONSUMER_WARPS);
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+
+    if (warp == NB_NAIVE_CONSUMER_WARPS) {
+        // ---- producer warp: one elected lane streams the source tiles through the ring ----
+        if (lane == 0) {
+            for (uint32_t t = 0; t < n_tiles; ++t) {
+                const uint32_t s = t % NB_NAIVE_STAGES;
+                const uint32_t use = t / NB_NAIVE_STAGES;
+                if (use > 0) mbar_wait(&empty[s], (use - 1) & 1);
+                mbar_expect_tx(&full[s], tile_bytes);
+                bulk_g2s(tiles + (size_t) s * tile_len, src + (size_t) t * tile_len, tile_bytes, &full[s]);
+            }
+        }
+        return;
+    }
+
+    // ---- consumer warps ----
+    constexpr int TPB = NB_NAIVE_CONSUMER_WARPS * 32;  // targets per pass per IPT slot
+    const uint64_t base = i_begin + (uint64_t) blockIdx.x * (TPB * IPT) + threadIdx.x;
+    double px[IPT], py[IPT], pz[IPT], accx[IPT], accy[IPT], accz[IPT];
+#pragma unroll
+    for (int k = 0; k < IPT; ++k) {
+        uint64_t i = base + (uint64_t) k * TPB;
+        if (i >= i_end) i = i_end - 1;
+        px[k] = x[i]; py[k] = y[i]; pz[k] = z[i];
+        accx[k] = accy[k] = accz[k] = 0.0;
+    }
+
+    for (uint32_t t = 0; t < n_tiles; ++t) {
+        const uint32_t s = t % NB_NAIVE_STAGES;
+        mbar_wait(&full[s], (t / NB_NAIVE_STAGES) & 1);
+        const double2 *tp = reinterpret_cast<const double2 *>(tiles + (size_t) s * tile_len);
+#pragma unroll 4
+        for (uint32_t j = 0; j < tile_len; ++j) {
+            const double2 xy = tp[3 * j + 0];
+            const double2 zm = tp[3 * j + 1];
+            const double2 cc = tp[3 * j + 2];
+#pragma unroll
+            for (int k = 0; k < IPT; ++k) {
+                const double rx = xy.x - px[k];
+                const double ry = xy.y - py[k];
+                const double rz = zm.x - pz[k];
+                double d2 = fma(rx, rx, eps2);
+                d2 = fma(ry, ry, d2);
+                d2 = fma(rz, rz, d2);
+                const double y0 = nb_rsqrt_seed(d2);
+                const double y2 = y0 * y0;
+                const double e = fma(-d2, y2, 1.0);
+                const double y3 = y2 * y0;
+                double q;
+                if (PRECISE) {
+                    const double p = fma(cc.y, e, cc.x);
+                    q = fma(p, e, zm.y);
+                } else {
+                    q = fma(cc.x, e, zm.y);
+                }
+                const double sfac = y3 * q;
+                accx[k] = fma(rx, sfac, accx[k]);
+                accy[k] = fma(ry, sfac, accy[k]);
+                accz[k] = fma(rz, sfac, accz[k]);
+            }
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&empty[s]);
+    }
+
+#pragma unroll
+    for (int k = 0; k < IPT; ++k) {
+        const uint64_t i = base + (uint64_t) k * TPB;
+        if (i < i_end) {
+            ax[i] = accx[k] * G;
+            ay[i] = accy[k] * G;
+            az[i] = accz[k] * G;
+        }
+    }
+}
+
+// DFMA-chain microbenchmark: 8 independent chains per thread, 2 flops per DFMA.
+__global__ void __launch_bounds__(256) fp64_peak_kernel(double *out, int iters, double a, double b) {
+    double v0 = threadIdx.x, v1 = v0 + 1, v2 = v0 + 2, v3 = v0 + 3, v4 = v0 + 4, v5 = v0 + 5, v6 = v0 + 6, v7 = v0 + 7;
+    for (int i = 0; i < iters; ++i) {
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+            v0 = fma(v0, a, b); v1 = fma(v1, a, b); v2 = fma(v2, a, b); v3 = fma(v3, a, b);
+            v4 = fma(v4, a, b); v5 = fma(v5, a, b); v6 = fma(v6, a, b); v7 = fma(v7, a, b);
+        }
+    }
+    out[(size_t) blockIdx.x * blockDim.x + threadIdx.x] = ((v0 + v1) + (v2 + v3)) + ((v4 + v5) + (v6 + v7));
+}
+
+template <int IPT, bool PRECISE>
+int launch_naive(nb_ctx *ctx, uint32_t n_tiles, uint32_t tile_len, uint64_t i_begin, uint64_t i_end) {
+    const uint64_t per_cta = (uint64_t) NB_NAIVE_CONSUMER_WARPS * 32 * IPT;
+    const uint64_t grid = (i_end - i_begin + per_cta - 1) / per_cta;
+    const size_t smem = 128 + (size_t) NB_NAIVE_STAGES * tile_len * sizeof(nb_src_rec);
+    auto kern = naive_accel_kernel<IPT, PRECISE>;
+    NB_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
+    kern<<<(unsigned) grid, NB_NAIVE_THREADS, smem, ctx->stream>>>(ctx->src, n_tiles, tile_len, ctx->x, ctx->y, ctx->z,
+                                                                   i_begin, i_end, ctx->cfg.epsilon2, ctx->cfg.G,
+                                                                   ctx->ax, ctx->ay, ctx->az);
+    NB_LAUNCH_CHECK(ctx);
+    return NB_OK;
+}
+
+}  // namespace
+
+int nbk_naive_accel(nb_ctx *ctx, uint64_t i_begin, uint64_t i_end) {
+    if (ctx->n == 0 || i_begin >= i_end) return NB_OK;
+    // --block_size -> shared-memory tile length (reference: tile = work-group = blockSize, NaiveAlgorithm.cpp:275-296)
+    uint32_t tile_len = (uint32_t) ctx->cfg.block_size;
+    if (tile_len < 16) tile_len = 16;
+    if (tile_len > 1024) tile_len = 1024;
+    tile_len = (tile_len + 3u) & ~3u;
+    const uint64_t n_pad = (ctx->n + tile_len - 1) / tile_len * tile_len;
+    if (n_pad > ctx->src_cap) {
+        NB_CHECK(nb_alloc(ctx, &ctx->src, n_pad + 1024));
+        ctx->src_cap = n_pad + 1024;
+    }
+    {
+        const unsigned threads = 256;
+        const unsigned blocks = (unsigned) ((n_pad + threads - 1) / threads);
+        pack_sources_kernel<<<blocks, threads, 0, ctx->stream>>>(ctx->m, ctx->x, ctx->y, ctx->z, ctx->src, ctx->n, n_pad);
+        NB_LAUNCH_CHECK(ctx);
+    }
+    const uint32_t n_tiles = (uint32_t) (n_pad / tile_len);
+    const int ipt = ctx->cfg.reserved[0] > 0 ? ctx->cfg.reserved[0] : 2;  // register blocking (tuning knob)
+    const bool precise = ctx->cfg.precise_rsqrt != 0;
+    if (ipt == 1) return precise ? launch_naive<1, true>(ctx, n_tiles, tile_len, i_begin, i_end)
+                                 : launch_naive<1, false>(ctx, n_tiles, tile_len, i_begin, i_end);
+    if (ipt == 4) return precise ? launch_naive<4, true>(ctx, n_tiles, tile_len, i_begin, i_end)
+                                 : launch_naive<4, false>(ctx, n_tiles, tile_len, i_begin, i_end);
+    return precise ? launch_naive<2, true>(ctx, n_tiles, tile_len, i_begin, i_end)
+                   : launch_naive<2, false>(ctx, n_tiles, tile_len, i_begin, i_end);
+}
+
+int nbk_fp64_peak(nb_ctx *ctx, double *tflops) {
+    const int blocks = ctx->sm_count * 8, threads = 256, iters = 4096;
+    double *buf = nullptr;
+    NB_CUDA(ctx, cudaMalloc(&buf, (size_t) blocks * threads * sizeof(double)));
+    cudaEvent_t e0, e1;
+    cudaEventCreate(&e0);
+    cudaEventCreate(&e1);
+    double best = 0;
+    for (int rep = 0; rep < 4; ++rep) {
+        cudaEventRecord(e0, ctx->stream);
+        fp64_peak_kernel<<<blocks, threads, 0, ctx->stream>>>(buf, iters, 1.0000001, 1e-9);
+        ctx->launches++;
+        cudaEventRecord(e1, ctx->stream);
+        cudaEventSynchronize(e1);
+        float ms = 0;
+        cudaEventElapsedTime(&ms, e0, e1);
+        double fl = 2.0 * 64.0 * iters * (double) blocks * threads;
+        double tf = fl / (ms * 1e-3) / 1e12;
+        if (rep > 0 && tf > best) best = tf;
+    }
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    cudaFree(buf);
+    cudaError_t err = cudaGetLastError();
+    if (err != cudaSuccess) return nb_fail(ctx, NB_ERR_CUDA, "fp64 peak kernel: %s", cudaGetErrorString(err));
+    *tflops = best;
+    return NB_OK;
+}

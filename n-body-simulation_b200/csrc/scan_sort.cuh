@@ -1,0 +1,241 @@
+// Hand-written device primitives used by the Barnes-Hut build: exclusive prefix sum over uint32 and a stable
+// LSD radix sort of (uint64 key, uint32 value) pairs.  Replaces the reference's serial single_task scan
+// (ParallelOctreeTopDownSubtrees.cpp:461-474), its O(S^2) prefix (:491-500) and the linear-search scatter (:512-532).
+#pragma once
+#include "common.cuh"
+
+namespace nbprim {
+namespace {  // internal linkage: this header is included by several translation units
+
+constexpr int SCAN_THREADS = 256;
+constexpr int SCAN_ITEMS = 8;
+constexpr int SCAN_TILE = SCAN_THREADS * SCAN_ITEMS;  // 2048 elements per block
+
+__device__ __forceinline__ uint32_t warp_incl_scan(uint32_t v) {
+    const int lane = threadIdx.x & 31;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        uint32_t t = __shfl_up_sync(0xffffffffu, v, o);
+        if (lane >= o) v += t;
+    }
+    return v;
+}
+
+// exclusive scan of one value per thread across a block of NT threads; returns exclusive prefix, total in *total
+template <int NT>
+__device__ __forceinline__ uint32_t block_excl_scan(uint32_t v, uint32_t *total, uint32_t *smem /* NT/32 + 1 */) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const uint32_t inc = warp_incl_scan(v);
+    if (lane == 31) smem[warp] = inc;
+    __syncthreads();
+    if (warp == 0) {
+        uint32_t w = lane < NT / 32 ? smem[lane] : 0;
+        uint32_t wi = warp_incl_scan(w);
+        if (lane < NT / 32) smem[lane] = wi - w;
+        if (lane == 31) smem[NT / 32] = wi;
+    }
+    __syncthreads();
+    const uint32_t res = smem[warp] + inc - v;
+    *total = smem[NT / 32];
+    __syncthreads();
+    return res;
+}
+
+// phase 1: per-tile sums
+__global__ void __launch_bounds__(SCAN_THREADS)
+scan_reduce_kernel(const uint32_t *__restrict__ in, uint64_t n, uint32_t *__restrict__ tile_sums) {
+    __shared__ uint32_t sm[SCAN_THREADS / 32 + 1];
+    const uint64_t base = (uint64_t) blockIdx.x * SCAN_TILE;
+    uint32_t s = 0;
+#pragma unroll
+    for (int k = 0; k < SCAN_ITEMS; ++k) {
+        const uint64_t i = base + (uint64_t) k * SCAN_THREADS + threadIdx.x;
+        if (i < n) s += in[i];
+    }
+    uint32_t tot;
+    block_excl_scan<SCAN_THREADS>(s, &tot, sm);
+    if (threadIdx.x == 0) tile_sums[blockIdx.x] = tot;
+}
+
+// phase 2: one block scans the tile sums in place (exclusive), writes the grand total to *total_out
+__global__ void __launch_bounds__(1024)
+scan_tiles_kernel(uint32_t *__restrict__ tile_sums, uint32_t n_tiles, uint32_t *__restrict__ total_out) {
+    __shared__ uint32_t sm[1024 / 32 + 1];
+    uint32_t carry = 0;
+    for (uint32_t base = 0; base < n_tiles; base += 1024) {
+        const uint32_t i = base + threadIdx.x;
+        const uint32_t v = i < n_tiles ? tile_sums[i] : 0;
+        uint32_t tot;
+        const uint32_t ex = block_excl_scan<1024>(v, &tot, sm);
+        if (i < n_tiles) tile_sums[i] = carry + ex;
+        carry += tot;
+    }
+    if (threadIdx.x == 0 && total_out) *total_out = carry;
+}
+
+// phase 3: per-tile exclusive scan + tile offset.  Thread-contiguous item layout for the local scan.
+__global__ void __launch_bounds__(SCAN_THREADS)
+scan_apply_kernel(const uint32_t *in, uint64_t n, const uint32_t *__restrict__ tile_offs, uint32_t *out) {  // in may alias out
+    __shared__ uint32_t sm[SCAN_THREADS / 32 + 1];
+    const uint64_t base = (uint64_t) blockIdx.x * SCAN_TILE + (uint64_t) threadIdx.x * SCAN_ITEMS;
+    uint32_t v[SCAN_ITEMS];
+    uint32_t s = 0;
+#pragma unroll
+    for (int k = 0; k < SCAN_ITEMS; ++k) {
+        v[k] = (base + k < n) ? in[base + k] : 0;
+        s += v[k];
+    }
+    uint32_t tot;
+    uint32_t ex = block_excl_scan<SCAN_THREADS>(s, &tot, sm) + tile_offs[blockIdx.x];
+#pragma unroll
+    for (int k = 0; k < SCAN_ITEMS; ++k) {
+        if (base + k < n) out[base + k] = ex;
+        ex += v[k];
+    }
+}
+
+inline uint64_t scan_tiles_for(uint64_t n) { return (n + SCAN_TILE - 1) / SCAN_TILE; }
+
+// out[i] = sum_{k<i} in[i] for i in [0,n); grand total written to *total_dev (device pointer, may be null).
+// tile_tmp: device scratch of scan_tiles_for(n) uint32.  in may alias out.
+inline int exclusive_scan_u32(nb_ctx *ctx, const uint32_t *in, uint32_t *out, uint64_t n, uint32_t *tile_tmp,
+                              uint32_t *total_dev) {
+    if (n == 0) {
+        if (total_dev) NB_CUDA(ctx, cudaMemsetAsync(total_dev, 0, sizeof(uint32_t), ctx->stream));
+        return NB_OK;
+    }
+    const uint32_t tiles = (uint32_t) scan_tiles_for(n);
+    scan_reduce_kernel<<<tiles, SCAN_THREADS, 0, ctx->stream>>>(in, n, tile_tmp);
+    NB_LAUNCH_CHECK(ctx);
+    scan_tiles_kernel<<<1, 1024, 0, ctx->stream>>>(tile_tmp, tiles, total_dev);
+    NB_LAUNCH_CHECK(ctx);
+    scan_apply_kernel<<<tiles, SCAN_THREADS, 0, ctx->stream>>>(in, n, tile_tmp, out);
+    NB_LAUNCH_CHECK(ctx);
+    return NB_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// Stable LSD radix sort, 8-bit digits.  Per pass: (1) per-tile digit histogram, (2) exclusive scan of the
+// digit-major histogram table, (3) stable scatter (warp-level MATCH.ANY ranking, warp-private counters).
+// ---------------------------------------------------------------------------------------------------------------
+constexpr int RS_THREADS = 256;
+constexpr int RS_WARPS = RS_THREADS / 32;
+constexpr int RS_ITEMS = 16;                      // keys per thread
+constexpr int RS_TILE = RS_THREADS * RS_ITEMS;    // 4096 keys per block
+constexpr int RS_BINS = 256;
+
+__global__ void __launch_bounds__(RS_THREADS)
+rs_hist_kernel(const uint64_t *__restrict__ keys, uint64_t n, int shift, uint32_t n_tiles,
+               uint32_t *__restrict__ hist /* [RS_BINS][n_tiles] */) {
+    __shared__ uint32_t h[RS_BINS];
+    h[threadIdx.x] = 0;
+    __syncthreads();
+    const uint64_t base = (uint64_t) blockIdx.x * RS_TILE;
+#pragma unroll 4
+    for (int k = 0; k < RS_ITEMS; ++k) {
+        const uint64_t i = base + (uint64_t) k * RS_THREADS + threadIdx.x;
+        if (i < n) atomicAdd(&h[(keys[i] >> shift) & 0xff], 1u);
+    }
+    __syncthreads();
+    hist[(size_t) threadIdx.x * n_tiles + blockIdx.x] = h[threadIdx.x];
+}
+
+template <bool IOTA_VALS>
+__global__ void __launch_bounds__(RS_THREADS)
+rs_scatter_kernel(const uint64_t *__restrict__ keys_in, const uint32_t *__restrict__ vals_in, uint64_t n, int shift,
+                  uint32_t n_tiles, const uint32_t *__restrict__ hist_scanned, uint64_t *__restrict__ keys_out,
+                  uint32_t *__restrict__ vals_out) {
+    __shared__ uint32_t cnt[RS_WARPS][RS_BINS];   // per-warp digit counts, then per-warp exclusive bases
+    __shared__ uint32_t gbase[RS_BINS];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    for (int b = threadIdx.x; b < RS_WARPS * RS_BINS; b += RS_THREADS) (&cnt[0][0])[b] = 0;
+    gbase[threadIdx.x] = hist_scanned[(size_t) threadIdx.x * n_tiles + blockIdx.x];
+    __syncthreads();
+
+    // warp w owns the contiguous sub-tile [w*512, (w+1)*512) of the tile, processed in 16 rounds of 32 (stable order)
+    const uint64_t wbase = (uint64_t) blockIdx.x * RS_TILE + (uint64_t) warp * (32 * RS_ITEMS);
+    uint64_t key[RS_ITEMS];
+    uint32_t rank[RS_ITEMS];
+    const uint32_t lt = (1u << lane) - 1u;
+#pragma unroll
+    for (int k = 0; k < RS_ITEMS; ++k) {
+        const uint64_t i = wbase + (uint64_t) k * 32 + lane;
+        const bool valid = i < n;
+        key[k] = valid ? keys_in[i] : ~0ull;
+        const uint32_t d = valid ? (uint32_t) ((key[k] >> shift) & 0xff) : 0x100u;  // invalid lanes never match a real digit
+        const uint32_t peers = __match_any_sync(0xffffffffu, d);
+        const int leader = __ffs(peers) - 1;
+        uint32_t prior = 0;
+        if (valid && lane == leader) {
+            prior = cnt[warp][d];
+            cnt[warp][d] = prior + __popc(peers);
+        }
+        prior = __shfl_sync(0xffffffffu, prior, leader);
+        rank[k] = prior + __popc(peers & lt);
+    }
+    __syncthreads();
+    // per-digit exclusive prefix across the warps of the block
+    {
+        const int b = threadIdx.x;  // one digit per thread
+        uint32_t run = 0;
+#pragma unroll
+        for (int w = 0; w < RS_WARPS; ++w) {
+            const uint32_t c = cnt[w][b];
+            cnt[w][b] = run;
+            run += c;
+        }
+    }
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < RS_ITEMS; ++k) {
+        const uint64_t i = wbase + (uint64_t) k * 32 + lane;
+        if (i < n) {
+            const uint32_t d = (uint32_t) ((key[k] >> shift) & 0xff);
+            const uint64_t pos = (uint64_t) gbase[d] + cnt[warp][d] + rank[k];
+            keys_out[pos] = key[k];
+            vals_out[pos] = IOTA_VALS ? (uint32_t) i : vals_in[i];
+        }
+    }
+}
+
+inline uint32_t rs_tiles_for(uint64_t n) { return (uint32_t) ((n + RS_TILE - 1) / RS_TILE); }
+// scratch requirement in uint32 elements: histogram table + scan tile sums
+inline size_t rs_scratch_elems(uint64_t n) {
+    const size_t hist = (size_t) RS_BINS * rs_tiles_for(n);
+    return hist + scan_tiles_for(hist) + 16;
+}
+
+// Sorts n (key, val) pairs on bits [0, key_bits).  vals_a == nullptr on input means "vals = 0..n-1".
+// Ping-pongs between (keys_a, vals_a) and (keys_b, vals_b); on return *keys_sorted / *vals_sorted point at the
+// buffers that hold the result.
+inline int radix_sort_pairs(nb_ctx *ctx, uint64_t *keys_a, uint32_t *vals_a, uint64_t *keys_b, uint32_t *vals_b,
+                            uint64_t n, int key_bits, uint32_t *scratch, uint64_t **keys_sorted,
+                            uint32_t **vals_sorted, bool iota_first) {
+    uint64_t *kin = keys_a, *kout = keys_b;
+    uint32_t *vin = vals_a, *vout = vals_b;
+    if (n == 0) { *keys_sorted = kin; *vals_sorted = vin; return NB_OK; }
+    const uint32_t tiles = rs_tiles_for(n);
+    const size_t hist_elems = (size_t) RS_BINS * tiles;
+    uint32_t *hist = scratch;
+    uint32_t *tile_tmp = scratch + hist_elems;
+    bool first = true;
+    for (int shift = 0; shift < key_bits; shift += 8) {
+        rs_hist_kernel<<<tiles, RS_THREADS, 0, ctx->stream>>>(kin, n, shift, tiles, hist);
+        NB_LAUNCH_CHECK(ctx);
+        NB_CHECK(exclusive_scan_u32(ctx, hist, hist, hist_elems, tile_tmp, nullptr));
+        if (first && iota_first)
+            rs_scatter_kernel<true><<<tiles, RS_THREADS, 0, ctx->stream>>>(kin, vin, n, shift, tiles, hist, kout, vout);
+        else
+            rs_scatter_kernel<false><<<tiles, RS_THREADS, 0, ctx->stream>>>(kin, vin, n, shift, tiles, hist, kout, vout);
+        NB_LAUNCH_CHECK(ctx);
+        first = false;
+        uint64_t *tk = kin; kin = kout; kout = tk;
+        uint32_t *tv = vin; vin = vout; vout = tv;
+    }
+    *keys_sorted = kin;
+    *vals_sorted = vin;
+    return NB_OK;
+}
+
+}  // namespace
+}  // namespace nbprim
