@@ -196,6 +196,10 @@ int nb_comm_init(nb_ctx *ctx, const uint8_t id[NB_COMM_ID_BYTES], int world_size
 /* slice of targets [begin, end) a rank owns (host-side logic; no GPU needed)                             */
 void nb_slice_bounds(uint64_t n, int world_size, int rank, uint64_t *begin, uint64_t *end);
 
+/* user events on the context's stream (CUDA events; bench.py brackets its timed region with them).  slot 0..7.  */
+int nb_event_record(nb_ctx *ctx, int slot);
+int nb_event_elapsed_ms(nb_ctx *ctx, int slot_begin, int slot_end, double *ms); /* synchronises on slot_end */
+
 /* ---- measurement helpers ---------------------------------------------------------------------------------- */
 /* DFMA-chain microbenchmark on the context's device: achieved fp64 TFLOP/s (2 flops per DFMA).           */
 int nb_measure_fp64_peak(nb_ctx *ctx, double *tflops);

@@ -51,7 +51,7 @@ EXPORTED_SYMBOLS = [
     "nb_op_naive_accelerations", "nb_op_barnes_hut_accelerations", "nb_bh_tree_info", "nb_bh_aabb",
     "nb_bh_export_canonical", "nb_bh_sorted_bodies", "nb_bh_enable_stats", "nb_bh_get_stats",
     "nb_util_group_by_subtree", "nb_enable_timers", "nb_get_timers", "nb_timer_name", "nb_comm_get_unique_id",
-    "nb_comm_init", "nb_slice_bounds", "nb_measure_fp64_peak", "nb_launch_count", "nb_device_pointers",
+    "nb_comm_init", "nb_slice_bounds", "nb_event_record", "nb_event_elapsed_ms", "nb_measure_fp64_peak", "nb_launch_count", "nb_device_pointers",
 ]
 
 _lib = None
@@ -114,6 +114,8 @@ def load_library():
     L.nb_comm_init.argtypes = [vp, C.POINTER(C.c_uint8), C.c_int, C.c_int]
     L.nb_slice_bounds.argtypes = [C.c_uint64, C.c_int, C.c_int, _u64p, _u64p]
     L.nb_slice_bounds.restype = None
+    L.nb_event_record.argtypes = [vp, C.c_int]
+    L.nb_event_elapsed_ms.argtypes = [vp, C.c_int, C.c_int, _dp]
     L.nb_measure_fp64_peak.argtypes = [vp, _dp]
     L.nb_launch_count.argtypes = [vp]
     L.nb_launch_count.restype = C.c_uint64
@@ -337,6 +339,14 @@ class Context:
         ms = np.zeros(NB_T_COUNT)
         self._ck(self.L.nb_get_timers(self.h, _d(ms)))
         return dict(zip(TIMER_NAMES, ms.tolist()))
+
+    def event_record(self, slot):
+        self._ck(self.L.nb_event_record(self.h, slot))
+
+    def event_elapsed_ms(self, a, b):
+        v = C.c_double()
+        self._ck(self.L.nb_event_elapsed_ms(self.h, a, b, C.byref(v)))
+        return v.value
 
     def measure_fp64_peak(self):
         v = C.c_double()

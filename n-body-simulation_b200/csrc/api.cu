@@ -89,6 +89,7 @@ int nb_create(const nb_config *cfg, nb_ctx **out) {
         return NB_ERR_CUDA;
     }
     for (int i = 0; i < 2 * NB_T_COUNT; ++i) cudaEventCreate(&ctx->ev[i]);
+    for (int i = 0; i < 8; ++i) cudaEventCreate(&ctx->user_ev[i]);
     *out = ctx;
     return NB_OK;
 }
@@ -105,6 +106,7 @@ void nb_destroy(nb_ctx *ctx) {
     nb_free(&ctx->anorm); nb_free(&ctx->src); nb_free(&ctx->e_partial);
     if (ctx->h_pinned) cudaFreeHost(ctx->h_pinned);
     for (int i = 0; i < 2 * NB_T_COUNT; ++i) cudaEventDestroy(ctx->ev[i]);
+    for (int i = 0; i < 8; ++i) cudaEventDestroy(ctx->user_ev[i]);
     cudaStreamDestroy(ctx->stream);
     delete ctx;
 }
@@ -375,6 +377,21 @@ const char *nb_timer_name(int t) {
     return (t >= 0 && t < NB_T_COUNT) ? names[t] : "";
 }
 
+int nb_event_record(nb_ctx *ctx, int slot) {
+    if (!ctx || slot < 0 || slot >= 8) return NB_ERR_INVALID;
+    NB_CUDA(ctx, cudaSetDevice(ctx->device));
+    NB_CUDA(ctx, cudaEventRecord(ctx->user_ev[slot], ctx->stream));
+    return NB_OK;
+}
+int nb_event_elapsed_ms(nb_ctx *ctx, int a, int b, double *ms) {
+    if (!ctx || !ms || a < 0 || a >= 8 || b < 0 || b >= 8) return NB_ERR_INVALID;
+    NB_CUDA(ctx, cudaEventSynchronize(ctx->user_ev[b]));
+    float f = 0;
+    NB_CUDA(ctx, cudaEventElapsedTime(&f, ctx->user_ev[a], ctx->user_ev[b]));
+    *ms = f;
+    return NB_OK;
+}
+
 int nb_measure_fp64_peak(nb_ctx *ctx, double *tflops) {
     if (!ctx || !tflops) return NB_ERR_INVALID;
     NB_CUDA(ctx, cudaSetDevice(ctx->device));
@@ -497,8 +514,10 @@ struct CanonSink {
     size_t k = 0;
     std::vector<uint32_t> *sorted = nullptr;
 };
-void canon_rec(const HostTree &t, uint32_t node, int depth, uint64_t phi, uint64_t plo, double edge, double mnx,
+// returns false when the node array is inconsistent (never expected; guards the host walk against garbage)
+bool canon_rec(const HostTree &t, uint32_t node, int depth, uint64_t phi, uint64_t plo, double edge, double mnx,
                double mny, double mnz, CanonSink &s) {
+    if (node >= t.M || depth > NB_MAX_TREE_DEPTH + 1) return false;
     const uint2 m = t.meta[node];
     const bool leaf = (m.y & NB_LEAF_FLAG) != 0;
     if (s.depth) {
@@ -513,13 +532,16 @@ void canon_rec(const HostTree &t, uint32_t node, int depth, uint64_t phi, uint64
     }
     s.k++;
     if (leaf) {
+        if ((m.y & ~NB_LEAF_FLAG) >= t.n) return false;
         if (s.sorted) s.sorted->push_back(t.perm[m.y & ~NB_LEAF_FLAG]);
-        return;
+        return true;
     }
+    if (m.x > t.M || m.x <= node) return false;
     uint32_t child_of_octant[8];
     for (int o = 0; o < 8; ++o) child_of_octant[o] = NB_LEAF_FLAG;  // marker: empty
     for (uint32_t c = node + 1; c < m.x;) {
         const uint2 mc = t.meta[c];
+        if (mc.x <= c || mc.x > m.x) return false;
         const uint32_t fb = (mc.y & NB_LEAF_FLAG) ? (mc.y & ~NB_LEAF_FLAG) : t.first_body[c];
         child_of_octant[rank_to_octant(host_digit(t, fb, depth))] = c;
         c = mc.x;
@@ -542,10 +564,11 @@ void canon_rec(const HostTree &t, uint32_t node, int depth, uint64_t phi, uint64
                 s.mass[k] = 0; s.comx[k] = 0; s.comy[k] = 0; s.comz[k] = 0;
             }
             s.k++;
-        } else {
-            canon_rec(t, child_of_octant[o], depth + 1, h2, l2, h, cx, cy, cz, s);
+        } else if (!canon_rec(t, child_of_octant[o], depth + 1, h2, l2, h, cx, cy, cz, s)) {
+            return false;
         }
     }
+    return true;
 }
 }  // namespace
 
@@ -560,7 +583,8 @@ int nb_bh_export_canonical(nb_ctx *ctx, uint32_t *depth, uint64_t *path_hi, uint
     HostTree t;
     NB_CHECK(fetch_tree(ctx, t));
     CanonSink s{depth, path_hi, path_lo, kind, body, count, edge, minx, miny, minz, mass, comx, comy, comz};
-    canon_rec(t, 0, 0, 0, 0, t.aabb[6], t.aabb[0], t.aabb[1], t.aabb[2], s);
+    if (!canon_rec(t, 0, 0, 0, 0, t.aabb[6], t.aabb[0], t.aabb[1], t.aabb[2], s))
+        return nb_fail(ctx, NB_ERR_INVALID, "nb_bh_export_canonical: inconsistent node array");
     return NB_OK;
 }
 
@@ -573,7 +597,8 @@ int nb_bh_sorted_bodies(nb_ctx *ctx, uint32_t *sorted_bodies) {
     order.reserve(t.n);
     CanonSink s{};
     s.sorted = &order;
-    canon_rec(t, 0, 0, 0, 0, t.aabb[6], t.aabb[0], t.aabb[1], t.aabb[2], s);
+    if (!canon_rec(t, 0, 0, 0, 0, t.aabb[6], t.aabb[0], t.aabb[1], t.aabb[2], s) || order.size() != t.n)
+        return nb_fail(ctx, NB_ERR_INVALID, "nb_bh_sorted_bodies: inconsistent node array");
     memcpy(sorted_bodies, order.data(), t.n * sizeof(uint32_t));
     return NB_OK;
 }

@@ -60,8 +60,7 @@ aabb_partial_kernel(const double *__restrict__ x, const double *__restrict__ y, 
 }
 
 __global__ void __launch_bounds__(256)
-aabb_final_kernel(const double *__restrict__ partial, int n_partials, double *__restrict__ out /* 7 */,
-                  uint32_t *__restrict__ flags) {
+aabb_final_kernel(const double *__restrict__ partial, int n_partials, double *__restrict__ out /* 7 */) {
     __shared__ double s[6][256];
     for (int c = 0; c < 6; ++c) {
         double v = 0.0;
@@ -102,7 +101,6 @@ aabb_final_kernel(const double *__restrict__ partial, int n_partials, double *__
         out[0] = min_x; out[1] = min_y; out[2] = min_z;
         out[3] = max_x; out[4] = max_y; out[5] = max_z;
         out[6] = maxEdgeLength;
-        flags[0] = 0; flags[1] = 0; flags[2] = 0; flags[3] = 0;
     }
 }
 
@@ -424,7 +422,7 @@ int nbk_bh_aabb(nb_ctx *ctx) {
     if (blocks < 1) blocks = 1;
     aabb_partial_kernel<<<blocks, 256, 0, ctx->stream>>>(ctx->x, ctx->y, ctx->z, n, b.aabb_partial);
     NB_LAUNCH_CHECK(ctx);
-    aabb_final_kernel<<<1, 256, 0, ctx->stream>>>(b.aabb_partial, blocks, b.aabb_dev, b.dev_flags);
+    aabb_final_kernel<<<1, 256, 0, ctx->stream>>>(b.aabb_partial, blocks, b.aabb_dev);
     NB_LAUNCH_CHECK(ctx);
     return NB_OK;
 }
@@ -437,6 +435,8 @@ int nbk_bh_build(nb_ctx *ctx) {
     NB_CHECK(nbk_bh_reserve(ctx));
     const unsigned g256 = (unsigned) ((n + 255) / 256), g128 = (unsigned) ((n + 127) / 128);
     nb_timer_scope total(ctx, NB_T_TREE_TOTAL);
+    // flags: [0] error bits, [1] internal node count, [2] max depth
+    NB_CUDA(ctx, cudaMemsetAsync(b.dev_flags, 0, 4 * sizeof(uint32_t), ctx->stream));
     {
         nb_timer_scope t(ctx, NB_T_AABB);
         NB_CHECK(nbk_bh_aabb(ctx));

@@ -70,6 +70,8 @@ extern "C" int nb_comm_get_unique_id(uint8_t id[NB_COMM_ID_BYTES]) {
 
 extern "C" int nb_comm_init(nb_ctx *ctx, const uint8_t id[NB_COMM_ID_BYTES], int world_size, int rank) {
     if (!ctx || world_size < 1 || rank < 0 || rank >= world_size) return nb_fail(ctx, NB_ERR_INVALID, "nb_comm_init: bad rank/world");
+    if (ctx->n > 0 && world_size != ctx->world)
+        return nb_fail(ctx, NB_ERR_INVALID, "nb_comm_init must be called before nb_set_bodies (buffers are sized per world)");
     nbk_comm_destroy(ctx);
     ctx->world = world_size;
     ctx->rank = rank;

@@ -90,6 +90,7 @@ struct nb_ctx {
     cudaEvent_t ev[2 * NB_T_COUNT] = {};
     bool ev_valid[NB_T_COUNT] = {};
     uint64_t launches = 0;
+    cudaEvent_t user_ev[8] = {};
     // comm
     void *nccl_comm = nullptr;
     int world = 1, rank = 0;

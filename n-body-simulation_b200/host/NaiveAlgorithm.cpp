@@ -1,0 +1,19 @@
+#include "NaiveAlgorithm.hpp"
+
+NaiveAlgorithm::NaiveAlgorithm(double dt, double tEnd, double visualizationStepWidth, std::string &outputDirectory)
+    : nBodyAlgorithm(dt, tEnd, visualizationStepWidth, outputDirectory) {
+    description = "Naive Algorithm";
+}
+
+void NaiveAlgorithm::computeAccelerations() { check(nb_naive_accel(ctx), "nb_naive_accel"); }
+
+void NaiveAlgorithm::startSimulation(const SimulationData &simulationData) {
+    openDevice(simulationData);
+    timer.addTimingSequence("Acceleration Kernel Time");
+    runTimeLoop(simulationData, [this]() {
+        computeAccelerations();
+        double ms[NB_T_COUNT];
+        check(nb_get_timers(ctx, ms), "nb_get_timers");
+        timer.addTimeToSequence("Acceleration Kernel Time", ms[NB_T_ACCEL]);
+    });
+}

@@ -1,0 +1,297 @@
+#include "nBodyAlgorithm.hpp"
+
+#include <unistd.h>
+
+#include <algorithm>
+#include <chrono>
+#include <cstdlib>
+#include <cstring>
+#include <ctime>
+#include <filesystem>
+#include <fstream>
+#include <iostream>
+#include <stdexcept>
+#include <thread>
+
+nBodyAlgorithm::nBodyAlgorithm(double dt_, double t_end_, double vs, std::string &outDir)
+    : outputDirectory(outDir), dt(dt_), t_end(t_end_), visualizationStepWidth(vs) {
+    nb_config defaults;
+    nb_config_default(&defaults);  // G in AU^3 kg^-1 day^-2, computed as the reference does (nBodyAlgorithm.hpp:55-61)
+    G = defaults.G;
+}
+
+nBodyAlgorithm::~nBodyAlgorithm() {
+    if (ctx) nb_destroy(ctx);
+}
+
+void nBodyAlgorithm::check(int status, const char *what) {
+    if (status == NB_OK) return;
+    std::string msg = std::string(what) + ": " + nb_status_string(status);
+    if (ctx && nb_last_error(ctx)[0]) msg += std::string(" (") + nb_last_error(ctx) + ")";
+    throw std::runtime_error(msg);
+}
+
+namespace {
+// single-node rendezvous for the NCCL unique id: rank 0 writes it to a file, the other ranks wait for it
+std::string commFilePath() {
+    if (const char *p = std::getenv("NBODY_COMM_FILE")) return p;
+    const char *port = std::getenv("MASTER_PORT");
+    return std::string("/tmp/nbody_b200_nccl_") + (port ? port : "0") + ".id";
+}
+}  // namespace
+
+void nBodyAlgorithm::openDevice(const SimulationData &d) {
+    if (!configuration::use_GPUs)
+        std::cout << "Note: --use_gpus=false is accepted but there is no CPU back end; running on the GPU." << std::endl;
+    nb_config cfg = configuration::toDeviceConfig(G);
+    check(nb_create(&cfg, &ctx), "nb_create");
+    if (configuration::worldSize > 1) {
+        uint8_t id[NB_COMM_ID_BYTES];
+        const std::string path = commFilePath();
+        if (configuration::rank == 0) {
+            check(nb_comm_get_unique_id(id), "nb_comm_get_unique_id");
+            const std::string tmp = path + ".tmp";
+            std::ofstream(tmp, std::ios::binary).write(reinterpret_cast<const char *>(id), sizeof id);
+            std::filesystem::rename(tmp, path);
+        } else {
+            for (int tries = 0; !std::filesystem::exists(path); ++tries) {
+                if (tries > 6000) throw std::runtime_error("timed out waiting for " + path);
+                std::this_thread::sleep_for(std::chrono::milliseconds(10));
+            }
+            std::ifstream(path, std::ios::binary).read(reinterpret_cast<char *>(id), sizeof id);
+        }
+        check(nb_comm_init(ctx, id, configuration::worldSize, configuration::rank), "nb_comm_init");
+        if (configuration::rank == 0) std::filesystem::remove(path);
+    }
+    check(nb_set_bodies(ctx, d.mass.size(), d.mass.data(), d.positions_x.data(), d.positions_y.data(),
+                        d.positions_z.data(), d.velocities_x.data(), d.velocities_y.data(), d.velocities_z.data()),
+          "nb_set_bodies");
+    check(nb_enable_timers(ctx, 1), "nb_enable_timers");
+    char name[256];
+    check(nb_device_name(ctx, name, sizeof name), "nb_device_name");
+    std::string device = name;
+    timer.setProperties(description, configuration::numberOfBodies, device);
+}
+
+void nBodyAlgorithm::computeEnergy(d_type::int_t currentStep) {
+    double e[4];
+    check(nb_energy(ctx, e), "nb_energy");
+    kineticEnergy[currentStep] = e[0];
+    potentialEnergy[currentStep] = e[1];
+    totalEnergy[currentStep] = e[2];
+    virialEquilibrium[currentStep] = e[3];
+}
+
+void nBodyAlgorithm::storeAccelerations(d_type::int_t currentStep) {
+    std::vector<double> &norms = acceleration[currentStep];
+    norms.resize(configuration::numberOfBodies);
+    check(nb_get_acceleration_norms(ctx, norms.data()), "nb_get_acceleration_norms");
+}
+
+void nBodyAlgorithm::adjustVelocities(const SimulationData &d) {
+    const std::size_t n = configuration::numberOfBodies;
+    double mass = 0, px = 0, py = 0, pz = 0;
+    for (std::size_t i = 0; i < n; ++i) {
+        mass += d.mass[i];
+        px += d.mass[i] * d.velocities_x[i];
+        py += d.mass[i] * d.velocities_y[i];
+        pz += d.mass[i] * d.velocities_z[i];
+    }
+    const double ux = px / mass, uy = py / mass, uz = pz / mass;
+    std::vector<double> &ox = velocities_x[0], &oy = velocities_y[0], &oz = velocities_z[0];
+    for (std::size_t i = 0; i < n; ++i) {
+        ox[i] -= ux;
+        oy[i] -= uy;
+        oz[i] -= uz;
+    }
+}
+
+void nBodyAlgorithm::runTimeLoop(const SimulationData &d, const std::function<void()> &forces) {
+    const std::size_t n = configuration::numberOfBodies;
+    timer.addTimingSequence("Leapfrog Part 1");
+    timer.addTimingSequence("Leapfrog Part 2");
+
+    // step 0 of the output: positions as read, velocities with the mean motion removed; the integrator itself starts
+    // from the unadjusted velocities already on the device
+    positions_x[0] = d.positions_x; positions_y[0] = d.positions_y; positions_z[0] = d.positions_z;
+    velocities_x[0] = d.velocities_x; velocities_y[0] = d.velocities_y; velocities_z[0] = d.velocities_z;
+    adjustVelocities(d);
+
+    double time = 0.0, timeSinceLastVisualization = 0.0;
+    d_type::int_t currentStep = 0;
+
+    forces();
+    if (configuration::compute_energy) computeEnergy(currentStep);
+    storeAccelerations(currentStep);
+    if (isOutputRank()) std::cout << "Finished initial step " << currentStep << std::endl << std::endl;
+
+    time += dt;
+    timeSinceLastVisualization += dt;
+    currentStep += 1;
+
+    double ms[NB_T_COUNT];
+    bool kickPending = false;  // second half-kick of the previous (non-visualised) step still to be applied
+    while (time <= t_end + 0.000001) {
+        const bool visualizeCurrentStep = std::abs(timeSinceLastVisualization - visualizationStepWidth) < 0.000001;
+
+        // kick-drift; when the previous step needed no output its closing half-kick rides along in the same pass
+        check(kickPending ? nb_leapfrog_part2_part1(ctx, dt) : nb_leapfrog_part1(ctx, dt), "leapfrog part 1");
+        kickPending = false;
+
+        if (visualizeCurrentStep) {
+            std::vector<double> &px = positions_x[currentStep], &py = positions_y[currentStep], &pz = positions_z[currentStep];
+            px.resize(n); py.resize(n); pz.resize(n);
+            check(nb_get_positions(ctx, px.data(), py.data(), pz.data()), "nb_get_positions");
+        }
+
+        forces();
+
+        const double next_time = time + dt;
+        const bool last_step = !(next_time <= t_end + 0.000001);
+        if (visualizeCurrentStep || last_step) {
+            check(nb_leapfrog_part2(ctx, dt), "leapfrog part 2");
+        } else {
+            kickPending = true;
+        }
+        check(nb_get_timers(ctx, ms), "nb_get_timers");
+        timer.addTimeToSequence("Leapfrog Part 1", ms[NB_T_LEAPFROG1]);
+        timer.addTimeToSequence("Leapfrog Part 2", kickPending ? 0.0 : ms[NB_T_LEAPFROG2]);
+
+        if (visualizeCurrentStep) {
+            if (isOutputRank()) std::cout << "Finished step " << currentStep << std::endl << std::endl;
+            storeAccelerations(currentStep);
+            std::vector<double> &vx = velocities_x[currentStep], &vy = velocities_y[currentStep], &vz = velocities_z[currentStep];
+            vx.resize(n); vy.resize(n); vz.resize(n);
+            check(nb_get_velocities(ctx, vx.data(), vy.data(), vz.data()), "nb_get_velocities");
+            if (configuration::compute_energy) computeEnergy(currentStep);
+            currentStep += 1;
+            timeSinceLastVisualization = 0.0;
+        }
+        time += dt;
+        timeSinceLastVisualization += dt;
+    }
+    check(nb_synchronize(ctx), "nb_synchronize");
+}
+
+// ---- output ------------------------------------------------------------------------------------------------------
+namespace {
+
+// orbit classes of https://pdssbn.astro.umd.edu/data_other/objclass.shtml plus STA/DWA/PLA/SAT, numbered as the
+// reference does (nBodyAlgorithm.cpp:298-342); unknown -> 0
+int orbitClassId(const std::string &c) {
+    static const char *const names[] = {"AMO", "APO", "ATE", "IEO", "MCA", "IMB", "MBA", "OMB", "CEN",
+                                        "TJN", "TNO", "AST", "PAA", "HYA", "STA", "DWA", "PLA", "SAT"};
+    for (int i = 0; i < 18; ++i)
+        if (c == names[i]) return i + 1;
+    return 0;
+}
+
+void openArray(std::ofstream &f, const char *type, const char *name, int components) {
+    f << "<DataArray type=\"" << type << "\" Name=\"" << name << "\" NumberOfComponents=\"" << components
+      << "\" format=\"ascii\">" << '\n';
+}
+void openField(std::ofstream &f, const char *name) {
+    f << "<DataArray type=\"Float64\" Name=\"" << name << "\" NumberOfTuples=\"1\" format=\"ascii\">" << '\n';
+}
+const char *const kCloseArray = "</DataArray>";
+
+}  // namespace
+
+void nBodyAlgorithm::generateParaViewOutput(const SimulationData &d) {
+    if (!isOutputRank()) return;
+    // <vs_dir>/<ctime with ' ' -> '_'>/ exactly like the reference (nBodyAlgorithm.cpp:132-140)
+    std::time_t now = std::time(nullptr);
+    std::string stamp = std::ctime(&now);
+    std::replace(stamp.begin(), stamp.end(), ' ', '_');
+    stamp.pop_back();  // trailing newline
+    const std::string base = outputDirectory + '/' + stamp + '/';
+    std::filesystem::create_directories(base);
+    lastOutputPath = base;
+
+    timer.exportJSON(base + "times.json");
+    outputLastState(base + "lastState.csv");
+
+    std::ofstream pvd(base + "/simulation" + ".pvd");
+    pvd << "<?xml version=\"1.0\"?>" << '\n'
+        << "<VTKFile type=\"Collection\" version=\"0.1\" byte_order=\"LittleEndian\" compressor=\"vtkZLibDataCompressor\">"
+        << '\n' << "<Collection>" << '\n';
+
+    const bool energy = configuration::compute_energy;
+    for (d_type::int_t step = 0; step < positions_x.size(); ++step) {
+        const std::string name = "simulation_step" + std::to_string(step) + ".vtp";
+        pvd << "<DataSet timestep=\"" << step << "\" group=\"\" part=\"0\" file=\"" << name << "\"/>" << '\n';
+
+        std::ofstream f(base + name);
+        const std::vector<double> &px = positions_x[step], &py = positions_y[step], &pz = positions_z[step];
+        const std::vector<double> &vx = velocities_x[step], &vy = velocities_y[step], &vz = velocities_z[step];
+        const std::vector<double> &an = acceleration[step];
+        const std::size_t n = px.size();
+
+        f << "<?xml version=\"1.0\"?>" << '\n'
+          << "<VTKFile type=\"PolyData\" version=\"0.1\" byte_order=\"LittleEndian\" header_type=\"UInt64\">" << '\n'
+          << "<PolyData>" << '\n'
+          << "<Piece NumberOfPoints=\"" << n << "\" NumberOfVerts=\"" << n << "\">" << '\n'
+          << "<Points>" << '\n';
+        openArray(f, "Float64", "position", 3);
+        for (std::size_t j = 0; j < n; ++j) f << px.at(j) << " " << py.at(j) << " " << pz.at(j) << '\n';
+        f << kCloseArray << '\n' << "</Points>" << '\n' << "<PointData>" << '\n';
+
+        openArray(f, "Int32", "body_id", 1);
+        for (std::size_t j = 0; j < n; ++j) f << j << '\n';
+        f << kCloseArray << '\n';
+
+        openArray(f, "Float64", "velocity", 3);
+        for (std::size_t j = 0; j < vx.size(); ++j) f << vx.at(j) << " " << vy.at(j) << " " << vz.at(j) << '\n';
+        f << kCloseArray << '\n';
+
+        openArray(f, "Float64", "acceleration", 1);
+        for (std::size_t j = 0; j < n; ++j) f << an[j] << '\n';
+        f << kCloseArray << '\n';
+
+        openArray(f, "Float64", "mass", 1);
+        for (double m : d.mass) f << m << '\n';
+        f << kCloseArray << '\n';
+
+        // names as space separated ASCII codes terminated by " 0" (nBodyAlgorithm.cpp:344-351)
+        openArray(f, "String", "name", 1);
+        for (const std::string &nm : d.names) {
+            for (char c : nm) f << (int) c << ' ';
+            f << " 0" << '\n';
+        }
+        f << kCloseArray << '\n';
+
+        openArray(f, "Int32", "orbit_class", 1);
+        for (const std::string &c : d.body_classes) f << orbitClassId(c) << '\n';
+        f << kCloseArray << '\n' << "</PointData>" << '\n' << "<Verts>" << '\n';
+
+        f << "<DataArray type=\"Int64\" Name=\"offsets\">" << '\n';
+        for (std::size_t j = 1; j <= n; ++j) f << std::to_string(j) << ' ';
+        f << '\n' << kCloseArray << '\n';
+        f << "<DataArray type=\"Int64\" Name=\"connectivity\">" << '\n';
+        for (std::size_t j = 0; j < n; ++j) f << std::to_string(j) << ' ';
+        f << '\n' << kCloseArray << '\n' << "</Verts>" << '\n' << "</Piece>" << '\n' << "<FieldData>" << '\n';
+
+        // energies are 0 when --energy is off (nBodyAlgorithm.cpp:253-284)
+        openField(f, "kinetic energy");
+        if (energy) f << kineticEnergy[step] << '\n'; else f << 0 << '\n';
+        f << kCloseArray << '\n';
+        openField(f, "potential energy");
+        if (energy) f << potentialEnergy[step] << '\n'; else f << 0 << '\n';
+        f << kCloseArray << '\n';
+        openField(f, "total energy");
+        if (energy) f << totalEnergy[step] << '\n'; else f << 0 << '\n';
+        f << kCloseArray << '\n';
+        openField(f, "virial equilibrium");
+        if (energy) f << virialEquilibrium[step] << '\n'; else f << 0 << '\n';
+        f << kCloseArray << '\n' << "</FieldData>" << '\n' << "</PolyData>" << '\n' << "</VTKFile>" << '\n';
+    }
+    pvd << "</Collection>" << '\n' << "</VTKFile>" << '\n';
+}
+
+void nBodyAlgorithm::outputLastState(const std::string &path) {
+    std::ofstream csv(path);
+    const d_type::int_t last = positions_x.size() - 1;
+    csv << "position_x, position_y, position_z \n";
+    const std::vector<double> &px = positions_x[last], &py = positions_y[last], &pz = positions_z[last];
+    for (std::size_t j = 0; j < px.size(); ++j) csv << px.at(j) << "," << py.at(j) << "," << pz.at(j) << '\n';
+}

@@ -1,0 +1,64 @@
+// Base class of the two simulation back ends: same public surface as the reference's nBodyAlgorithm
+// (reference src/simulationBackend/nBodyAlgorithm.hpp:19-187) -- description, dt / t_end / visualisation step, G,
+// the per-step snapshot maps, energy maps, generateParaViewOutput / outputLastState / adjustVelocities -- but the
+// sycl::queue + sycl::buffer arguments are gone: device state lives in an nb_ctx (include/nbody_b200.h) owned by the
+// object, and computeEnergy / storeAccelerations read it through the C ABI.
+#pragma once
+#include <cmath>
+#include <functional>
+#include <map>
+#include <string>
+#include <vector>
+
+#include "Configuration.hpp"
+#include "SimulationData.hpp"
+#include "TimeMeasurement.hpp"
+#include "nbody_b200.h"
+
+class nBodyAlgorithm {
+public:
+    std::string description;  // "Naive Algorithm" / "Barnes-Hut Algorithm"
+    std::string outputDirectory;
+    double dt;
+    double t_end;
+    double visualizationStepWidth;
+    double G;
+
+    TimeMeasurement timer;
+
+    // visualised step -> per-body values
+    std::map<d_type::int_t, std::vector<double>> positions_x, positions_y, positions_z;
+    std::map<d_type::int_t, std::vector<double>> velocities_x, velocities_y, velocities_z;
+    std::map<d_type::int_t, std::vector<double>> acceleration;  // |a|
+    std::map<d_type::int_t, double> kineticEnergy, potentialEnergy, totalEnergy, virialEquilibrium;
+
+    nBodyAlgorithm(double dt, double t_end, double visualizationStepWidth, std::string &outputDirectory);
+    virtual ~nBodyAlgorithm();
+
+    virtual void startSimulation(const SimulationData &simulationData) = 0;
+
+    void generateParaViewOutput(const SimulationData &simulationData);
+    void outputLastState(const std::string &path);
+
+    // energies of the current device state, stored under currentStep (reference nBodyAlgorithm.cpp:11-86)
+    void computeEnergy(d_type::int_t currentStep);
+    // |a| of the current device accelerations (reference nBodyAlgorithm.cpp:88-102)
+    void storeAccelerations(d_type::int_t currentStep);
+    // removes the mass-weighted mean velocity from the step-0 OUTPUT velocities only (reference :104-127)
+    void adjustVelocities(const SimulationData &simulationData);
+
+    // where generateParaViewOutput wrote its files (empty before the call)
+    std::string lastOutputPath;
+    bool isOutputRank() const { return configuration::rank == 0; }
+
+protected:
+    nb_ctx *ctx = nullptr;
+
+    // creates the device context from the configuration globals, joins the NCCL communicator when launched with one
+    // process per GPU, uploads the bodies (unadjusted velocities) and registers the device name with the timer
+    void openDevice(const SimulationData &simulationData);
+    void check(int status, const char *what);
+    // the time loop shared by both back ends (reference NaiveAlgorithm.cpp:82-259 = BarnesHutAlgorithm.cpp:102-277);
+    // `forces` evaluates the accelerations of the current positions and records its own timing sequences
+    void runTimeLoop(const SimulationData &simulationData, const std::function<void()> &forces);
+};

@@ -1,5 +1,6 @@
 """Developer GPU check: parity vs the oracle + quick timings.  Run under gpurun; writes gpurun_out/dev_check.log."""
-import importlib, os, sys, time, traceback
+import importlib, os, sys, time, traceback, faulthandler
+faulthandler.dump_traceback_later(int(os.environ.get("HANG_S", "500")), exit=True)
 import numpy as np
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "oracle"))
