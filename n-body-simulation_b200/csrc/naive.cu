@@ -170,17 +170,23 @@ naive_accel_kernel(const nb_src_rec *__restrict__ src, uint32_t n_tiles, uint32_
     }
 }
 
-// DFMA-chain microbenchmark: 8 independent chains per thread, 2 flops per DFMA.
-__global__ void __launch_bounds__(256) fp64_peak_kernel(double *out, int iters, double a, double b) {
-    double v0 = threadIdx.x, v1 = v0 + 1, v2 = v0 + 2, v3 = v0 + 3, v4 = v0 + 4, v5 = v0 + 5, v6 = v0 + 6, v7 = v0 + 7;
+// DFMA-chain microbenchmark: CHAINS independent dependent-FMA chains per thread, 2 flops per DFMA.
+template <int CHAINS>
+__global__ void __launch_bounds__(1024) fp64_peak_kernel(double *out, int iters, double a, double b) {
+    double v[CHAINS];
+#pragma unroll
+    for (int c = 0; c < CHAINS; ++c) v[c] = threadIdx.x + c;
     for (int i = 0; i < iters; ++i) {
 #pragma unroll
         for (int u = 0; u < 8; ++u) {
-            v0 = fma(v0, a, b); v1 = fma(v1, a, b); v2 = fma(v2, a, b); v3 = fma(v3, a, b);
-            v4 = fma(v4, a, b); v5 = fma(v5, a, b); v6 = fma(v6, a, b); v7 = fma(v7, a, b);
+#pragma unroll
+            for (int c = 0; c < CHAINS; ++c) v[c] = fma(v[c], a, b);
         }
     }
-    out[(size_t) blockIdx.x * blockDim.x + threadIdx.x] = ((v0 + v1) + (v2 + v3)) + ((v4 + v5) + (v6 + v7));
+    double s = 0;
+#pragma unroll
+    for (int c = 0; c < CHAINS; ++c) s += v[c];
+    out[(size_t) blockIdx.x * blockDim.x + threadIdx.x] = s;
 }
 
 template <int IPT, bool PRECISE>
@@ -229,24 +235,32 @@ int nbk_naive_accel(nb_ctx *ctx, uint64_t i_begin, uint64_t i_end) {
 }
 
 int nbk_fp64_peak(nb_ctx *ctx, double *tflops) {
-    const int blocks = ctx->sm_count * 8, threads = 256, iters = 4096;
+    // best of several launch shapes (chains per thread x CTA size), each timed over >= 10 ms so clocks settle
     double *buf = nullptr;
-    NB_CUDA(ctx, cudaMalloc(&buf, (size_t) blocks * threads * sizeof(double)));
+    const size_t max_threads = (size_t) ctx->sm_count * 2048;
+    NB_CUDA(ctx, cudaMalloc(&buf, max_threads * sizeof(double)));
     cudaEvent_t e0, e1;
     cudaEventCreate(&e0);
     cudaEventCreate(&e1);
     double best = 0;
-    for (int rep = 0; rep < 4; ++rep) {
-        cudaEventRecord(e0, ctx->stream);
-        fp64_peak_kernel<<<blocks, threads, 0, ctx->stream>>>(buf, iters, 1.0000001, 1e-9);
-        ctx->launches++;
-        cudaEventRecord(e1, ctx->stream);
-        cudaEventSynchronize(e1);
-        float ms = 0;
-        cudaEventElapsedTime(&ms, e0, e1);
-        double fl = 2.0 * 64.0 * iters * (double) blocks * threads;
-        double tf = fl / (ms * 1e-3) / 1e12;
-        if (rep > 0 && tf > best) best = tf;
+    const int shapes[4][2] = {{8, 256}, {16, 256}, {8, 512}, {16, 1024}};  // {chains, threads}
+    for (int sidx = 0; sidx < 4; ++sidx) {
+        const int chains = shapes[sidx][0], threads = shapes[sidx][1];
+        const int blocks = ctx->sm_count * (2048 / threads);
+        const int iters = 16384 / chains * 8;
+        for (int rep = 0; rep < 3; ++rep) {
+            cudaEventRecord(e0, ctx->stream);
+            if (chains == 8) fp64_peak_kernel<8><<<blocks, threads, 0, ctx->stream>>>(buf, iters, 1.0000001, 1e-9);
+            else fp64_peak_kernel<16><<<blocks, threads, 0, ctx->stream>>>(buf, iters, 1.0000001, 1e-9);
+            ctx->launches++;
+            cudaEventRecord(e1, ctx->stream);
+            cudaEventSynchronize(e1);
+            float ms = 0;
+            cudaEventElapsedTime(&ms, e0, e1);
+            const double fl = 2.0 * 8.0 * chains * iters * (double) blocks * threads;
+            const double tf = fl / (ms * 1e-3) / 1e12;
+            if (rep > 0 && tf > best) best = tf;
+        }
     }
     cudaEventDestroy(e0);
     cudaEventDestroy(e1);

@@ -220,23 +220,28 @@ def test_tree_with_cloud_far_from_origin(nb, oracle, ctx):
     ctx.bh_build()
     t = oracle.Tree(m, x, y, z)
     a = ctx.bh_aabb()
-    assert a[0] == 0.0 and a[4] == 0.0
+    assert np.array_equal(a, t.aabb())
+    assert a[0] == 0.0 and a[6] == x.max()       # x in [0, max]: the origin is the low corner of the longest axis
+    assert a[1] < y.min() and a[4] > 0.0         # y spans [min, 0], then grown symmetrically to the cube
     assert_same_tree(ctx.bh_export_canonical(), t.canonical())
 
 
-def test_deep_tree_uses_second_key_word(nb, oracle, ctx):
-    """Pairs closer than edge * 2^-21 need the 42-level path (key_lo)."""
+def test_deep_tree_uses_second_key_word(nb, oracle):
+    """Pairs closer than edge * 2^-21 need the 42-level path (key_lo).  Long single-child chains need more node
+    storage than 16 N (the reference would overflow silently): --storage_size_param=64 on both sides."""
+    ctx = nb.Context(device=0, storage_size_param=64)
     m, x, y, z, *_ = nb.generators.uniform_sphere(300, seed=10)
     x = np.concatenate([x, x[:40] + 3e-9]); y = np.concatenate([y, y[:40] - 2e-9]); z = np.concatenate([z, z[:40] + 1e-9])
     m = np.concatenate([m, m[:40]])
     ctx.set_bodies(m, x, y, z)
     ctx.bh_build()
-    t = oracle.Tree(m, x, y, z)
+    t = oracle.Tree(m, x, y, z, storage_param=64)
     assert t.max_depth > 21 and ctx.bh_tree_info().max_depth == t.max_depth
     assert_same_tree(ctx.bh_export_canonical(), t.canonical())
     ctx.set_theta(0.5)
     ctx.bh_accel()
     assert relerr(ctx.accelerations(), t.accel(0.5)) <= TOL
+    ctx.close()
 
 
 def test_coincident_bodies_are_reported(nb, ctx):
