@@ -130,6 +130,10 @@ def default_config(**overrides):
     for k, v in overrides.items():
         if k == "ipt":
             cfg.reserved[0] = int(v)
+        elif k == "single_phase_walk":
+            cfg.reserved[1] = int(v)
+        elif k == "naive_variant":
+            cfg.reserved[2] = int(v)
         else:
             setattr(cfg, k, v)
     return cfg

@@ -479,8 +479,7 @@ struct HostTree {
     uint64_t n = 0, M = 0;
     std::vector<uint2> meta;
     std::vector<double> com, msum;
-    std::vector<uint32_t> first_body, body_count, perm;
-    std::vector<uint64_t> hi, lo;
+    std::vector<uint32_t> body_count, perm;
     double aabb[7];
 };
 int fetch_tree(nb_ctx *ctx, HostTree &t) {
@@ -488,21 +487,15 @@ int fetch_tree(nb_ctx *ctx, HostTree &t) {
     NB_CHECK(nb_synchronize(ctx));
     t.n = ctx->n;
     t.M = b.num_nodes;
-    t.meta.resize(t.M); t.com.resize(4 * t.M); t.msum.resize(3 * t.M);
-    t.first_body.resize(t.M); t.body_count.resize(t.M); t.perm.resize(t.n); t.hi.resize(t.n); t.lo.resize(t.n);
+    t.meta.resize(t.M); t.com.resize(4 * t.M); t.msum.resize(4 * t.M);
+    t.body_count.resize(t.M); t.perm.resize(t.n);
     NB_CUDA(ctx, cudaMemcpy(t.meta.data(), b.meta, t.M * sizeof(uint2), cudaMemcpyDeviceToHost));
     NB_CUDA(ctx, cudaMemcpy(t.com.data(), b.com, 4 * t.M * sizeof(double), cudaMemcpyDeviceToHost));
-    NB_CUDA(ctx, cudaMemcpy(t.msum.data(), b.msum, 3 * t.M * sizeof(double), cudaMemcpyDeviceToHost));
-    NB_CUDA(ctx, cudaMemcpy(t.first_body.data(), b.first_body, t.M * sizeof(uint32_t), cudaMemcpyDeviceToHost));
+    NB_CUDA(ctx, cudaMemcpy(t.msum.data(), b.msum, 4 * t.M * sizeof(double), cudaMemcpyDeviceToHost));
     NB_CUDA(ctx, cudaMemcpy(t.body_count.data(), b.body_count, t.M * sizeof(uint32_t), cudaMemcpyDeviceToHost));
     NB_CUDA(ctx, cudaMemcpy(t.perm.data(), b.perm, t.n * sizeof(uint32_t), cudaMemcpyDeviceToHost));
-    NB_CUDA(ctx, cudaMemcpy(t.hi.data(), b.key_hi, t.n * sizeof(uint64_t), cudaMemcpyDeviceToHost));
-    NB_CUDA(ctx, cudaMemcpy(t.lo.data(), b.key_hi_alt, t.n * sizeof(uint64_t), cudaMemcpyDeviceToHost));
     NB_CUDA(ctx, cudaMemcpy(t.aabb, b.aabb_dev, 7 * sizeof(double), cudaMemcpyDeviceToHost));
     return NB_OK;
-}
-inline uint32_t host_digit(const HostTree &t, uint32_t body, int level) {
-    return level < 21 ? (uint32_t) ((t.hi[body] >> (60 - 3 * level)) & 7) : (uint32_t) ((t.lo[body] >> (60 - 3 * (level - 21))) & 7);
 }
 inline uint32_t rank_to_octant(uint32_t r) {  // rank = 4u + 2b + (1-r)  ->  octant = 4u + 2r + b
     const uint32_t u = r >> 2, bk = (r >> 1) & 1, rt = 1 - (r & 1);
@@ -524,16 +517,16 @@ bool canon_rec(const HostTree &t, uint32_t node, int depth, uint64_t phi, uint64
         const size_t k = s.k;
         s.depth[k] = depth; s.path_hi[k] = phi; s.path_lo[k] = plo;
         s.kind[k] = leaf ? 1 : 2;
-        s.body[k] = leaf ? t.perm[m.y & ~NB_LEAF_FLAG] : (uint32_t) t.n;
+        s.body[k] = leaf ? t.perm[m.y & NB_PAYLOAD_MASK] : (uint32_t) t.n;
         s.count[k] = t.body_count[node];
         s.edge[k] = edge; s.minx[k] = mnx; s.miny[k] = mny; s.minz[k] = mnz;
         s.mass[k] = t.com[4 * (size_t) node + 3];
-        s.comx[k] = t.msum[3 * (size_t) node]; s.comy[k] = t.msum[3 * (size_t) node + 1]; s.comz[k] = t.msum[3 * (size_t) node + 2];
+        s.comx[k] = t.msum[4 * (size_t) node]; s.comy[k] = t.msum[4 * (size_t) node + 1]; s.comz[k] = t.msum[4 * (size_t) node + 2];
     }
     s.k++;
     if (leaf) {
-        if ((m.y & ~NB_LEAF_FLAG) >= t.n) return false;
-        if (s.sorted) s.sorted->push_back(t.perm[m.y & ~NB_LEAF_FLAG]);
+        if ((m.y & NB_PAYLOAD_MASK) >= t.n) return false;
+        if (s.sorted) s.sorted->push_back(t.perm[m.y & NB_PAYLOAD_MASK]);
         return true;
     }
     if (m.x > t.M || m.x <= node) return false;
@@ -542,8 +535,7 @@ bool canon_rec(const HostTree &t, uint32_t node, int depth, uint64_t phi, uint64
     for (uint32_t c = node + 1; c < m.x;) {
         const uint2 mc = t.meta[c];
         if (mc.x <= c || mc.x > m.x) return false;
-        const uint32_t fb = (mc.y & NB_LEAF_FLAG) ? (mc.y & ~NB_LEAF_FLAG) : t.first_body[c];
-        child_of_octant[rank_to_octant(host_digit(t, fb, depth))] = c;
+        child_of_octant[rank_to_octant((mc.y >> NB_DIGIT_SHIFT) & 7u)] = c;
         c = mc.x;
     }
     const double h = edge / 2;  // ParallelOctreeTopDownSubtrees.cpp:256

@@ -18,10 +18,10 @@
 //   3. delta[i] = common-prefix digits of sorted neighbours.  Body i is the FIRST body of the internal cells of depth
 //      delta[i-1]+1 .. delta[i]; an exclusive scan of those counts gives every node its index in a DFS pre-order
 //      array (internal chain of body i, then leaf i).  Empty leaves are implied, never materialised.
-//   4. one thread per body emits its chain + leaf: skip links (first node after the subtree) and parent links by
-//      galloping searches over the sorted keys.
-//   5. centre of mass bottom-up with arrival counters weighted by body count: the last arriving child sums all
-//      children of its parent in octant order (deterministic, bit-identical to the reference's order).
+//   4. one thread per body emits its chain + leaf: skip links (first node after the subtree) by galloping searches
+//      over the sorted keys; each node records its visit rank inside its parent.
+//   5. centre of mass level by level, deepest first (one launch per depth, no atomics): a node sums its children in
+//      octant order (deterministic, bit-identical to the reference's order).
 #include "scan_sort.cuh"
 
 #define NB_NONE 0xffffffffu
@@ -223,8 +223,7 @@ delta_kernel(const uint64_t *__restrict__ hi, const uint64_t *__restrict__ lo, u
 __global__ void __launch_bounds__(128)
 emit_kernel(const uint64_t *__restrict__ hi, const uint64_t *__restrict__ lo, const int32_t *__restrict__ delta,
             const uint32_t *__restrict__ base, uint64_t n, uint64_t cap_nodes, uint32_t *__restrict__ flags,
-            uint2 *__restrict__ meta, uint32_t *__restrict__ parent, uint32_t *__restrict__ first_body,
-            uint32_t *__restrict__ body_count, uint32_t *__restrict__ arrive, uint32_t *__restrict__ leaf_node) {
+            uint2 *__restrict__ meta, uint32_t *__restrict__ body_count, uint32_t *__restrict__ leaf_node) {
     const uint64_t i = (uint64_t) blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     const uint64_t total_internal = flags[1];
@@ -241,20 +240,6 @@ emit_kernel(const uint64_t *__restrict__ hi, const uint64_t *__restrict__ lo, co
     const uint64_t head = i + b;          // first node that starts at body i
     const uint64_t leaf = head + c;
 
-    // parent of the head: the depth-d_prev cell that contains bodies i-1 and i; its first body by galloping left
-    uint32_t head_parent = NB_NONE;
-    if (i > 0) {
-        uint64_t f = i - 1;  // shares d_prev digits with i by definition
-        uint64_t step = 1;
-        while (f >= step && share_prefix(hi[f - step], lo[f - step], hi_i, lo_i, d_prev)) { f -= step; step <<= 1; }
-        while (step > 1) {
-            step >>= 1;
-            if (f >= step && share_prefix(hi[f - step], lo[f - step], hi_i, lo_i, d_prev)) f -= step;
-        }
-        const int d_before_f = f > 0 ? delta[f - 1] : -1;
-        head_parent = (uint32_t) (f + base[f] + (uint64_t) (d_prev - d_before_f - 1));
-    }
-
     // chain of internal nodes first-bodied by i, deepest first so the right boundary only moves outwards
     uint64_t r = i + 1;  // i+1 shares d_cur digits when c > 0
     for (int k = (int) c - 1; k >= 0; --k) {
@@ -267,90 +252,94 @@ emit_kernel(const uint64_t *__restrict__ hi, const uint64_t *__restrict__ lo, co
         }
         const uint64_t node = head + k;
         const uint64_t skip = r + 1 < n ? (r + 1) + base[r + 1] : M;
-        meta[node] = make_uint2((uint32_t) skip, (uint32_t) d);
-        first_body[node] = (uint32_t) i;
+        const uint32_t dig = d > 0 ? digit_at(hi_i, lo_i, d - 1) : 0u;  // visit rank of this cell inside its parent
+        meta[node] = make_uint2((uint32_t) skip, (dig << NB_DIGIT_SHIFT) | (uint32_t) d);
         body_count[node] = (uint32_t) (r - i + 1);
-        arrive[node] = 0;
-        parent[node] = k > 0 ? (uint32_t) (node - 1) : head_parent;
     }
-    meta[leaf] = make_uint2((uint32_t) (leaf + 1), NB_LEAF_FLAG | (uint32_t) i);
-    first_body[leaf] = (uint32_t) i;
+    const int leaf_parent_depth = d_cur > d_prev ? d_cur : d_prev;  // -1 only when N == 1
+    const uint32_t leaf_dig = leaf_parent_depth >= 0 ? digit_at(hi_i, lo_i, leaf_parent_depth) : 0u;
+    meta[leaf] = make_uint2((uint32_t) (leaf + 1), NB_LEAF_FLAG | (leaf_dig << NB_DIGIT_SHIFT) | (uint32_t) i);
     body_count[leaf] = 1;
-    parent[leaf] = c > 0 ? (uint32_t) (leaf - 1) : head_parent;
     leaf_node[i] = (uint32_t) leaf;
 }
 
 // ---- 5. centre of mass ------------------------------------------------------------------------------------------------------
 // leaf: prepareCenterOfMass (BarnesHutOctree.cpp:216-226); internal: the octant-ordered sum of :299-317.
-__global__ void __launch_bounds__(128)
-com_kernel(uint64_t n, const uint32_t *__restrict__ flags_in, const double *__restrict__ sx, const double *__restrict__ sy,
-           const double *__restrict__ sz, const double *__restrict__ sm, const uint64_t *__restrict__ hi,
-           const uint64_t *__restrict__ lo, const uint32_t *__restrict__ leaf_node, const uint2 *meta,
-           const uint32_t *__restrict__ parent, const uint32_t *__restrict__ first_body,
-           const uint32_t *__restrict__ body_count, uint32_t *arrive, double *com, double *msum) {
-    const uint64_t i = (uint64_t) blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    if (flags_in[0] & NB_FLAG_POOL) return;
-    uint32_t cur = leaf_node[i];
-    {
-        const double m = sm[i], px = sx[i], py = sy[i], pz = sz[i];
-        double *c4 = com + 4 * (size_t) cur;
-        double *s3 = msum + 3 * (size_t) cur;
-        s3[0] = __dmul_rn(px, m); s3[1] = __dmul_rn(py, m); s3[2] = __dmul_rn(pz, m);
-        // the reference's traversal divides the stored sum by the mass (BarnesHutAlgorithm.cpp:351-353), also for
-        // body leaves: (x*m)/m, which is not always x.  Store that quotient once instead of dividing per visit.
-        c4[0] = __ddiv_rn(s3[0], m); c4[1] = __ddiv_rn(s3[1], m); c4[2] = __ddiv_rn(s3[2], m); c4[3] = m;
-    }
-    uint32_t my_count = 1;
-    while (true) {
-        const uint32_t p = parent[cur];
-        if (p == NB_NONE) break;
-        __threadfence();
-        const uint32_t total = body_count[p];
-        const uint32_t old = atomicAdd(&arrive[p], my_count);
-        if (old + my_count != total) break;
-        __threadfence();
-        // last arrival: every child of p is final.  Collect them by visit rank, then sum in octant order.
-        const uint2 mp = meta[p];
-        const int depth = (int) mp.y;
-        double vx[8], vy[8], vz[8], vm[8];
-#pragma unroll
-        for (int r = 0; r < 8; ++r) { vx[r] = 0; vy[r] = 0; vz[r] = 0; vm[r] = 0; }
-        uint32_t ch = p + 1;
-        while (ch < mp.x) {
-            const uint2 mc = __ldcg(&meta[ch]);
-            const uint32_t fb = (mc.y & NB_LEAF_FLAG) ? (mc.y & ~NB_LEAF_FLAG) : first_body[ch];
-            const uint32_t rank = digit_at(hi[fb], lo[fb], depth);
-            const double cm = __ldcg(com + 4 * (size_t) ch + 3);
-            const double cx = __ldcg(msum + 3 * (size_t) ch + 0);
-            const double cy = __ldcg(msum + 3 * (size_t) ch + 1);
-            const double cz = __ldcg(msum + 3 * (size_t) ch + 2);
-#pragma unroll
-            for (int r = 0; r < 8; ++r)
-                if (rank == (uint32_t) r) { vx[r] = cx; vy[r] = cy; vz[r] = cz; vm[r] = cm; }
-            ch = mc.x;
-        }
-        // octant code o = 4u + 2r + b  <->  visit rank 4u + 2b + (1-r):  octants 0..7 are ranks 1,3,0,2,5,7,4,6
-        const int rank_of_octant[8] = {1, 3, 0, 2, 5, 7, 4, 6};
-        double sumMasses = 0, cx = 0, cy = 0, cz = 0;
-#pragma unroll
-        for (int o = 0; o < 8; ++o) {
-            const int r = rank_of_octant[o];
-            cx = __dadd_rn(cx, vx[r]);
-            cy = __dadd_rn(cy, vy[r]);
-            cz = __dadd_rn(cz, vz[r]);
-            sumMasses = __dadd_rn(sumMasses, vm[r]);
-        }
-        double *s3 = msum + 3 * (size_t) p;
-        s3[0] = cx; s3[1] = cy; s3[2] = cz;
-        double *c4 = com + 4 * (size_t) p;
-        c4[0] = __ddiv_rn(cx, sumMasses); c4[1] = __ddiv_rn(cy, sumMasses); c4[2] = __ddiv_rn(cz, sumMasses);
-        c4[3] = sumMasses;
-        my_count = total;
-        cur = p;
-    }
+// Level-synchronous, deepest level first: one launch per depth, one thread per body; the thread owns the internal node
+// of that depth whose first body it is (if any).  No locks, flags, atomics or fences (the reference spins on
+// SUM_MASSES != 0 inside one work-group, :263-384): kernel boundaries order the levels.  Every node writes
+//   msum4[n] = {sum m*x, sum m*y, sum m*z, sum m}   (the reference's massCenters_* / sumOfMasses; what parents read)
+//   com[n]   = {sums / mass, mass}                   (the quotient the reference forms per visit, BarnesHutAlgorithm.cpp:351-353)
+//   comf[n]  = fp32(com - root centre)               (walk phase of the traversal)
+struct root_centre { double x, y, z; };
+__device__ __forceinline__ void store_node(double *com, float *comf, double *msum4, uint32_t node, double sx, double sy,
+                                           double sz, double m, const root_centre &o) {
+    double2 *s2 = reinterpret_cast<double2 *>(msum4 + 4 * (size_t) node);
+    s2[0] = make_double2(sx, sy);
+    s2[1] = make_double2(sz, m);
+    const double cx = __ddiv_rn(sx, m), cy = __ddiv_rn(sy, m), cz = __ddiv_rn(sz, m);
+    double2 *c2 = reinterpret_cast<double2 *>(com + 4 * (size_t) node);
+    c2[0] = make_double2(cx, cy);
+    c2[1] = make_double2(cz, m);
+    reinterpret_cast<float4 *>(comf)[node] = make_float4((float) (cx - o.x), (float) (cy - o.y), (float) (cz - o.z), 0.0f);
 }
 
+__global__ void __launch_bounds__(256)
+com_leaf_kernel(uint64_t n, const uint32_t *__restrict__ flags_in, const double *__restrict__ sx,
+                const double *__restrict__ sy, const double *__restrict__ sz, const double *__restrict__ sm,
+                const uint32_t *__restrict__ leaf_node, double *__restrict__ com, float *__restrict__ comf,
+                double *__restrict__ msum4, const double *__restrict__ aabb) {
+    const uint64_t i = (uint64_t) blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n || (flags_in[0] & NB_FLAG_POOL)) return;
+    const double half = 0.5 * aabb[6];
+    const root_centre origin{aabb[0] + half, aabb[1] + half, aabb[2] + half};
+    const double m = sm[i];
+    store_node(com, comf, msum4, leaf_node[i], __dmul_rn(sx[i], m), __dmul_rn(sy[i], m), __dmul_rn(sz[i], m), m, origin);
+}
+
+__global__ void __launch_bounds__(256)
+com_level_kernel(int depth, uint64_t n, const uint32_t *__restrict__ flags_in, const int32_t *__restrict__ delta,
+                 const uint32_t *__restrict__ base, const uint2 *__restrict__ meta, double *com, float *comf,
+                 double *msum4, const double *__restrict__ aabb) {
+    // flags[2] = deepest leaf = 1 + deepest internal node: nothing to do for the levels below the tree
+    if ((uint32_t) depth >= flags_in[2] || (flags_in[0] & NB_FLAG_POOL)) return;
+    const uint64_t i = (uint64_t) blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const int d_cur = delta[i];
+    if (depth > d_cur) return;
+    const int d_prev = i > 0 ? delta[i - 1] : -1;
+    if (depth <= d_prev) return;
+    const uint32_t p = (uint32_t) (i + base[i] + (uint64_t) (depth - d_prev - 1));
+    const uint32_t end = meta[p].x;
+    double vx[8], vy[8], vz[8], vm[8];
+#pragma unroll
+    for (int r = 0; r < 8; ++r) { vx[r] = 0; vy[r] = 0; vz[r] = 0; vm[r] = 0; }
+    uint32_t ch = p + 1;
+    while (ch < end) {  // children: leaves or depth+1 nodes finished by the previous launch
+        const uint2 mc = meta[ch];
+        const double2 *s2 = reinterpret_cast<const double2 *>(msum4 + 4 * (size_t) ch);
+        const double2 a = s2[0], b = s2[1];
+        const uint32_t rank = (mc.y >> NB_DIGIT_SHIFT) & 7u;
+#pragma unroll
+        for (int r = 0; r < 8; ++r)
+            if (rank == (uint32_t) r) { vx[r] = a.x; vy[r] = a.y; vz[r] = b.x; vm[r] = b.y; }
+        ch = mc.x > ch ? mc.x : end;  // skip links always point forward
+    }
+    // octant code o = 4u + 2r + b  <->  visit rank 4u + 2b + (1-r):  octants 0..7 are ranks 1,3,0,2,5,7,4,6
+    const int rank_of_octant[8] = {1, 3, 0, 2, 5, 7, 4, 6};
+    double sumMasses = 0, cx = 0, cy = 0, cz = 0;
+#pragma unroll
+    for (int o = 0; o < 8; ++o) {
+        const int r = rank_of_octant[o];
+        cx = __dadd_rn(cx, vx[r]);
+        cy = __dadd_rn(cy, vy[r]);
+        cz = __dadd_rn(cz, vz[r]);
+        sumMasses = __dadd_rn(sumMasses, vm[r]);
+    }
+    const double half = 0.5 * aabb[6];
+    const root_centre origin{aabb[0] + half, aabb[1] + half, aabb[2] + half};
+    store_node(com, comf, msum4, p, cx, cy, cz, sumMasses, origin);
+}
 
 }  // namespace
 
@@ -383,12 +372,10 @@ int nbk_bh_reserve(nb_ctx *ctx) {
     NB_CHECK(nb_alloc(ctx, &b.asz, nb));
     NB_CHECK(nb_alloc(ctx, &b.visits, nb));
     NB_CHECK(nb_alloc(ctx, &b.com, 4 * cap_nodes));
-    NB_CHECK(nb_alloc(ctx, &b.msum, 3 * cap_nodes));
+    NB_CHECK(nb_alloc(ctx, &b.comf, 4 * cap_nodes));
+    NB_CHECK(nb_alloc(ctx, &b.msum, 4 * cap_nodes));
     NB_CHECK(nb_alloc(ctx, &b.meta, cap_nodes));
-    NB_CHECK(nb_alloc(ctx, &b.parent, cap_nodes));
-    NB_CHECK(nb_alloc(ctx, &b.first_body, cap_nodes));
     NB_CHECK(nb_alloc(ctx, &b.body_count, cap_nodes));
-    NB_CHECK(nb_alloc(ctx, &b.arrive, cap_nodes));
     const size_t scratch = nbprim::rs_scratch_elems(nb) + nbprim::scan_tiles_for(nb) + 64;
     NB_CHECK(nb_alloc(ctx, &b.hist, scratch));
     NB_CHECK(nb_alloc(ctx, &b.aabb_dev, 8));
@@ -407,8 +394,8 @@ void nbk_bh_release(nb_ctx *ctx) {
     nb_free(&b.key_hi); nb_free(&b.key_lo); nb_free(&b.key_hi_alt); nb_free(&b.perm); nb_free(&b.perm_alt);
     nb_free(&b.sx); nb_free(&b.sy); nb_free(&b.sz); nb_free(&b.sm); nb_free(&b.delta); nb_free(&b.chain_cnt);
     nb_free(&b.chain_base); nb_free(&b.leaf_node); nb_free(&b.asx); nb_free(&b.asy); nb_free(&b.asz);
-    nb_free(&b.visits); nb_free(&b.com); nb_free(&b.msum); nb_free(&b.meta); nb_free(&b.parent);
-    nb_free(&b.first_body); nb_free(&b.body_count); nb_free(&b.arrive); nb_free(&b.hist); nb_free(&b.aabb_dev);
+    nb_free(&b.visits); nb_free(&b.com); nb_free(&b.comf); nb_free(&b.msum); nb_free(&b.meta); 
+    nb_free(&b.body_count); nb_free(&b.hist); nb_free(&b.aabb_dev);
     nb_free(&b.aabb_partial); nb_free(&b.dev_flags); nb_free(&b.stat_totals);
     b.cap_bodies = b.cap_nodes = 0;
     b.built = false;
@@ -431,7 +418,7 @@ int nbk_bh_build(nb_ctx *ctx) {
     nb_bh_state &b = ctx->bh;
     const uint64_t n = ctx->n;
     if (n == 0) return nb_fail(ctx, NB_ERR_INVALID, "nb_bh_build: no bodies");
-    if (n >= 0x7fffffffull) return nb_fail(ctx, NB_ERR_UNSUPPORTED, "nb_bh_build: N must be < 2^31");
+    if (n >= (1ull << NB_DIGIT_SHIFT)) return nb_fail(ctx, NB_ERR_UNSUPPORTED, "nb_bh_build: N must be < 2^28");
     NB_CHECK(nbk_bh_reserve(ctx));
     const unsigned g256 = (unsigned) ((n + 255) / 256), g128 = (unsigned) ((n + 127) / 128);
     nb_timer_scope total(ctx, NB_T_TREE_TOTAL);
@@ -469,14 +456,19 @@ int nbk_bh_build(nb_ctx *ctx) {
         uint32_t *tile_tmp = b.hist;  // scan scratch (sort is finished)
         NB_CHECK(nbprim::exclusive_scan_u32(ctx, b.chain_cnt, b.chain_base, n, tile_tmp, b.dev_flags + 1));
         emit_kernel<<<g128, 128, 0, ctx->stream>>>(hi, lo, b.delta, b.chain_base, n, b.cap_nodes, b.dev_flags, b.meta,
-                                                   b.parent, b.first_body, b.body_count, b.arrive, b.leaf_node);
+                                                   b.body_count, b.leaf_node);
         NB_LAUNCH_CHECK(ctx);
     }
     {
         nb_timer_scope t(ctx, NB_T_COM);
-        com_kernel<<<g128, 128, 0, ctx->stream>>>(n, b.dev_flags, b.sx, b.sy, b.sz, b.sm, hi, lo, b.leaf_node, b.meta,
-                                                  b.parent, b.first_body, b.body_count, b.arrive, b.com, b.msum);
+        com_leaf_kernel<<<g256, 256, 0, ctx->stream>>>(n, b.dev_flags, b.sx, b.sy, b.sz, b.sm, b.leaf_node, b.com, b.comf,
+                                                       b.msum, b.aabb_dev);
         NB_LAUNCH_CHECK(ctx);
+        for (int depth = NB_MAX_TREE_DEPTH - 1; depth >= 0; --depth) {
+            com_level_kernel<<<g256, 256, 0, ctx->stream>>>(depth, n, b.dev_flags, b.delta, b.chain_base, b.meta, b.com,
+                                                            b.comf, b.msum, b.aabb_dev);
+            NB_LAUNCH_CHECK(ctx);
+        }
     }
     b.built = true;
     return NB_OK;

@@ -22,8 +22,11 @@ struct __align__(16) nb_src_rec {
 // [2,0,3,1,6,4,7,5], BarnesHutAlgorithm.cpp:370-385).  40 bytes of traversal payload per node:
 //   com[4*n+0..2] = centre of mass (already divided by the mass), com[4*n+3] = mass     (32 B)
 //   meta[n].x     = index of the first node AFTER this node's subtree ("skip link")
-//   meta[n].y     = body leaf: 0x80000000 | sorted index of the body;  internal node: depth        ( 8 B)
+//   meta[n].y     = bit 31: body leaf; bits 28-30: visit rank of the node inside its parent;
+//                   bits 0-27: sorted index of the body (leaf) or depth (internal node)              ( 8 B)
 #define NB_LEAF_FLAG 0x80000000u
+#define NB_DIGIT_SHIFT 28
+#define NB_PAYLOAD_MASK 0x0fffffffu
 
 struct nb_bh_state {
     // per-body, sorted order
@@ -36,13 +39,10 @@ struct nb_bh_state {
     uint32_t *leaf_node = nullptr;                           // node index of the leaf of sorted body i
     // per-node
     double *com = nullptr;                                   // 4 doubles per node
-    double *msum = nullptr;                                  // 3 doubles per node: mass-weighted sums (reference's massCenters_*)
+    float *comf = nullptr;                                   // 4 floats per node: COM relative to the root centre, fp32 (walk phase)
+    double *msum = nullptr;                                  // 4 doubles per node: {sum m*x, sum m*y, sum m*z, sum m} (reference's massCenters_* / sumOfMasses)
     uint2 *meta = nullptr;
-    uint32_t *parent = nullptr;
-    uint32_t *first_body = nullptr;                          // sorted index of the first body in the node's cell
     uint32_t *body_count = nullptr;
-    uint32_t *arrive = nullptr;                              // COM pass arrival counters
-    uint8_t *nchild = nullptr;
     // sort scratch
     uint32_t *hist = nullptr;
     void *scan_tmp = nullptr;

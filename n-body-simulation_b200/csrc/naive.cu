@@ -71,8 +71,8 @@ __global__ void pack_sources_kernel(const double *__restrict__ m, const double *
     out[i] = r;
 }
 
-template <int IPT, bool PRECISE>
-__global__ void __launch_bounds__(NB_NAIVE_THREADS, 2)
+template <int IPT, bool PRECISE, int UNROLL, int MINB>
+__global__ void __launch_bounds__(NB_NAIVE_THREADS, MINB)
 naive_accel_kernel(const nb_src_rec *__restrict__ src, uint32_t n_tiles, uint32_t tile_len,
                    const double *__restrict__ x, const double *__restrict__ y, const double *__restrict__ z,
                    uint64_t i_begin, uint64_t i_end, double eps2, double G, double *__restrict__ ax,
@@ -125,7 +125,7 @@ naive_accel_kernel(const nb_src_rec *__restrict__ src, uint32_t n_tiles, uint32_
         const uint32_t s = t % NB_NAIVE_STAGES;
         mbar_wait(&full[s], (t / NB_NAIVE_STAGES) & 1);
         const double2 *tp = reinterpret_cast<const double2 *>(tiles + (size_t) s * tile_len);
-#pragma unroll 4
+#pragma unroll(UNROLL)
         for (uint32_t j = 0; j < tile_len; ++j) {
             const double2 xy = tp[3 * j + 0];
             const double2 zm = tp[3 * j + 1];
@@ -189,12 +189,12 @@ __global__ void __launch_bounds__(1024) fp64_peak_kernel(double *out, int iters,
     out[(size_t) blockIdx.x * blockDim.x + threadIdx.x] = s;
 }
 
-template <int IPT, bool PRECISE>
+template <int IPT, bool PRECISE, int UNROLL = 4, int MINB = 2>
 int launch_naive(nb_ctx *ctx, uint32_t n_tiles, uint32_t tile_len, uint64_t i_begin, uint64_t i_end) {
     const uint64_t per_cta = (uint64_t) NB_NAIVE_CONSUMER_WARPS * 32 * IPT;
     const uint64_t grid = (i_end - i_begin + per_cta - 1) / per_cta;
     const size_t smem = 128 + (size_t) NB_NAIVE_STAGES * tile_len * sizeof(nb_src_rec);
-    auto kern = naive_accel_kernel<IPT, PRECISE>;
+    auto kern = naive_accel_kernel<IPT, PRECISE, UNROLL, MINB>;
     NB_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
     kern<<<(unsigned) grid, NB_NAIVE_THREADS, smem, ctx->stream>>>(ctx->src, n_tiles, tile_len, ctx->x, ctx->y, ctx->z,
                                                                    i_begin, i_end, ctx->cfg.epsilon2, ctx->cfg.G,
@@ -226,6 +226,21 @@ int nbk_naive_accel(nb_ctx *ctx, uint64_t i_begin, uint64_t i_end) {
     const uint32_t n_tiles = (uint32_t) (n_pad / tile_len);
     const int ipt = ctx->cfg.reserved[0] > 0 ? ctx->cfg.reserved[0] : 2;  // register blocking (tuning knob)
     const bool precise = ctx->cfg.precise_rsqrt != 0;
+    // tuning variants (reserved[2]): {IPT, UNROLL, MINB}; 0 = default
+    switch (precise ? ctx->cfg.reserved[2] : 0) {
+        case 1: return launch_naive<1, true, 8, 2>(ctx, n_tiles, tile_len, i_begin, i_end);
+        case 2: return launch_naive<2, true, 2, 2>(ctx, n_tiles, tile_len, i_begin, i_end);
+        case 3: return launch_naive<2, true, 4, 3>(ctx, n_tiles, tile_len, i_begin, i_end);
+        case 4: return launch_naive<2, true, 4, 4>(ctx, n_tiles, tile_len, i_begin, i_end);
+        case 5: return launch_naive<2, true, 8, 2>(ctx, n_tiles, tile_len, i_begin, i_end);
+        case 6: return launch_naive<4, true, 1, 2>(ctx, n_tiles, tile_len, i_begin, i_end);
+        case 7: return launch_naive<4, true, 2, 2>(ctx, n_tiles, tile_len, i_begin, i_end);
+        case 8: return launch_naive<4, true, 2, 3>(ctx, n_tiles, tile_len, i_begin, i_end);
+        case 9: return launch_naive<4, true, 4, 1>(ctx, n_tiles, tile_len, i_begin, i_end);
+        case 10: return launch_naive<2, true, 4, 1>(ctx, n_tiles, tile_len, i_begin, i_end);
+        case 11: return launch_naive<1, true, 4, 4>(ctx, n_tiles, tile_len, i_begin, i_end);
+        default: break;
+    }
     if (ipt == 1) return precise ? launch_naive<1, true>(ctx, n_tiles, tile_len, i_begin, i_end)
                                  : launch_naive<1, false>(ctx, n_tiles, tile_len, i_begin, i_end);
     if (ipt == 4) return precise ? launch_naive<4, true>(ctx, n_tiles, tile_len, i_begin, i_end)

@@ -138,6 +138,34 @@ def t_perf():
             print(gen, n, "wg", wg, "depth", info.max_depth, "internal/body %.3f" % (info.num_internal / n), {k: round(v, 3) for k, v in t.items() if v}, extra, flush=True)
             c.close()
 
+def t_naive_sweep():
+    section("naive sweep N=2^20")
+    n = 1 << 20
+    m, x, y, z, vx, vy, vz = nb.generators.plummer(n, seed=1)
+    names = {0: "ipt2 u4 b2 (default)", 1: "ipt1 u8 b2", 2: "ipt2 u2 b2", 3: "ipt2 u4 b3", 4: "ipt2 u4 b4", 5: "ipt2 u8 b2", 6: "ipt4 u1 b2",
+             7: "ipt4 u2 b2", 8: "ipt4 u2 b3", 9: "ipt4 u4 b1", 10: "ipt2 u4 b1", 11: "ipt1 u4 b4"}
+    for var in range(12):
+        for bs in (128, 256):
+            c = nb.Context(naive_variant=var, block_size=bs)
+            c.set_bodies(m, x, y, z, vx, vy, vz); c.enable_timers(True)
+            c.naive_accel(); ms = c.timers()["Acceleration Kernel Time"]
+            print("variant %2d %-22s bs=%d: %.2f ms  %.4e inter/s  %.2f TF(21)" % (var, names[var], bs, ms, n * n / ms * 1e3, 21.0 * n * n / ms * 1e3 / 1e12), flush=True)
+            c.close()
+
+
+def t_perf_bh():
+    section("perf bh")
+    for gen, n, theta in (("plummer", 1 << 20, 0.5), ("uniform_sphere", 1 << 22, 0.5), ("uniform_sphere", 1 << 24, 0.5)):
+        m, x, y, z, vx, vy, vz = getattr(nb.generators, gen)(n, seed=1)
+        for single in (1, 0):
+            for wg in (64, 128, 256):
+                c = nb.Context(theta=theta, wg_size_barnes_hut=wg, single_phase_walk=single); c.set_bodies(m, x, y, z, vx, vy, vz); c.enable_timers(True)
+                c.bh_build(); c.bh_accel(); c.synchronize()
+                c.bh_build(); c.bh_accel(); t = c.timers(); info = c.bh_tree_info()
+                print(gen, n, "single" if single else "two-phase", "wg", wg, "depth", info.max_depth, {k: round(v, 3) for k, v in t.items() if v}, flush=True)
+                c.close()
+
+
 if __name__ == "__main__":
     which = sys.argv[1:] or ["naive", "integrator", "bh_small", "perf"]
     for w in which:
