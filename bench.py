@@ -125,7 +125,7 @@ def run_reference(args, rank, world):
     nb = importlib.import_module("n-body-simulation_b200")
     n = args.n
     m, x, y, z, vx, vy, vz = nb.generators.plummer(n, seed=1)
-    threads = O.max_threads()
+    threads = host_threads(O)
     # bounded sample: R target rows against all N sources, sized for ~5 s per step from a short probe
     t0 = time.perf_counter()
     O.naive_accel(m, x, y, z, rows=(0, 64), nthreads=threads)
@@ -154,11 +154,19 @@ def run_reference(args, rank, world):
     print(json.dumps(line), flush=True)
 
 
+def host_threads(O):
+    """All host cores this process may use (torchrun exports OMP_NUM_THREADS=1, which would hide them)."""
+    try:
+        return max(O.max_threads(), len(os.sched_getaffinity(0)))
+    except AttributeError:
+        return max(O.max_threads(), os.cpu_count() or 1)
+
+
 def cpu_baseline(nb, n, seconds=12.0):
     sys.path.insert(0, os.path.join(ROOT, "oracle"))
     import oracle as O
     m, x, y, z, *_ = nb.generators.plummer(n, seed=1)
-    threads = O.max_threads()
+    threads = host_threads(O)
     t0 = time.perf_counter()
     O.naive_accel(m, x, y, z, rows=(0, 64), nthreads=threads)
     probe = time.perf_counter() - t0
@@ -173,14 +181,23 @@ def cpu_baseline(nb, n, seconds=12.0):
 
 
 # ---------------------------------------------------------------------------------------------------------------------
-def measure_bh(nb, torch, dist, args, rank, local_rank, world, dev, unique_id):
+def fresh_comm_id(nb, dist, rank, world):
+    """A new NCCL unique id per communicator (an id cannot be reused), created by rank 0 and broadcast by the host."""
+    if world == 1:
+        return None
+    ids = [nb.comm_unique_id() if rank == 0 else None]
+    dist.broadcast_object_list(ids, src=0)
+    return ids[0]
+
+
+def measure_bh(nb, torch, dist, args, rank, local_rank, world, dev):
     """Secondary metric: full Barnes-Hut steps/s (kick-drift, AABB, keys+sort, build, COM, traversal, kick)."""
     n = args.bh_n
     theta = 0.5
     m, x, y, z, vx, vy, vz = nb.generators.uniform_sphere(n, seed=1, velocity_scale=0.3)
     ctx = nb.Context(device=local_rank, theta=theta, wg_size_barnes_hut=128, world_size=world, rank=rank)
     if world > 1:
-        ctx.comm_init(unique_id, world, rank)
+        ctx.comm_init(fresh_comm_id(nb, dist, rank, world), world, rank)
     ctx.set_bodies(m, x, y, z, vx, vy, vz)
     dt = 1e-3  # days: bodies move, the tree changes every step
     ctx.bh_build(); ctx.bh_accel(); ctx.synchronize()
@@ -253,19 +270,15 @@ def run_ours(args, rank, local_rank, world):
     dev = torch.device("cuda", local_rank)
     torch.cuda.set_device(dev)
     dist = None
-    unique_id = None
     if world > 1:
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=dev)
-        ids = [nb.comm_unique_id() if rank == 0 else None]
-        dist.broadcast_object_list(ids, src=0)
-        unique_id = ids[0]
 
     n = args.n
     m, x, y, z, vx, vy, vz = nb.generators.plummer(n, seed=1)
     ctx = nb.Context(device=local_rank, block_size=NAIVE_TILE, world_size=world, rank=rank)
     if world > 1:
-        ctx.comm_init(unique_id, world, rank)
+        ctx.comm_init(fresh_comm_id(nb, dist, rank, world), world, rank)
     ctx.set_bodies(m, x, y, z, vx, vy, vz)
     dt = 1.0 / 24.0
 
@@ -343,7 +356,7 @@ def run_ours(args, rank, local_rank, world):
     if not args.no_bh:
         ctx.close()
         try:
-            bh = measure_bh(nb, torch, dist, args, rank, local_rank, world, dev, unique_id)
+            bh = measure_bh(nb, torch, dist, args, rank, local_rank, world, dev)
         except Exception as e:  # the headline line must survive a failure of the secondary metric
             bh = {"error": repr(e)}
     cpu = None

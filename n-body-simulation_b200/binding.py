@@ -130,8 +130,10 @@ def default_config(**overrides):
     for k, v in overrides.items():
         if k == "ipt":
             cfg.reserved[0] = int(v)
-        elif k == "single_phase_walk":
+        elif k in ("single_phase_walk", "bh_variant"):
             cfg.reserved[1] = int(v)
+        elif k == "walk_variant":
+            cfg.reserved[3] = int(v)
         elif k == "naive_variant":
             cfg.reserved[2] = int(v)
         else:

@@ -2,6 +2,7 @@
 // tree export for the parity tests.  No CPU fallback anywhere: every compute entry point launches sm_100a kernels.
 #include <math.h>
 #include <stdarg.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <algorithm>
@@ -458,8 +459,10 @@ int nb_bh_get_stats(nb_ctx *ctx, uint64_t *total_visits, uint64_t *total_accepts
     if (!ctx || !ctx->bh.built) return nb_fail(ctx, NB_ERR_INVALID, "nb_bh_get_stats: no tree");
     NB_CUDA(ctx, cudaSetDevice(ctx->device));
     NB_CHECK(nb_synchronize(ctx));
-    unsigned long long t[2];
+    unsigned long long t[8];
     NB_CUDA(ctx, cudaMemcpy(t, ctx->bh.stat_totals, sizeof t, cudaMemcpyDeviceToHost));
+    if (getenv("NB_DEBUG_STATS"))
+        fprintf(stderr, "[nb stats] visits %llu accepts %llu rounds %llu items %llu mixed %llu ilist %llu\n", t[0], t[1], t[2], t[3], t[4], t[5]);
     if (total_visits) *total_visits = t[0];
     if (total_accepts) *total_accepts = t[1];
     if (visits_per_body) {

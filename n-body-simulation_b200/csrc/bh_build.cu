@@ -22,6 +22,8 @@
 //      over the sorted keys; each node records its visit rank inside its parent.
 //   5. centre of mass level by level, deepest first (one launch per depth, no atomics): a node sums its children in
 //      octant order (deterministic, bit-identical to the reference's order).
+#include <algorithm>
+
 #include "scan_sort.cuh"
 
 #define NB_NONE 0xffffffffu
@@ -300,45 +302,52 @@ com_leaf_kernel(uint64_t n, const uint32_t *__restrict__ flags_in, const double 
 __global__ void __launch_bounds__(256)
 com_level_kernel(int depth, uint64_t n, const uint32_t *__restrict__ flags_in, const int32_t *__restrict__ delta,
                  const uint32_t *__restrict__ base, const uint2 *__restrict__ meta, double *com, float *comf,
-                 double *msum4, const double *__restrict__ aabb) {
+                 double *msum4, uint32_t *__restrict__ ctab, const double *__restrict__ aabb) {
     // flags[2] = deepest leaf = 1 + deepest internal node: nothing to do for the levels below the tree
     if ((uint32_t) depth >= flags_in[2] || (flags_in[0] & NB_FLAG_POOL)) return;
-    const uint64_t i = (uint64_t) blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    const int d_cur = delta[i];
-    if (depth > d_cur) return;
-    const int d_prev = i > 0 ? delta[i - 1] : -1;
-    if (depth <= d_prev) return;
-    const uint32_t p = (uint32_t) (i + base[i] + (uint64_t) (depth - d_prev - 1));
-    const uint32_t end = meta[p].x;
-    double vx[8], vy[8], vz[8], vm[8];
-#pragma unroll
-    for (int r = 0; r < 8; ++r) { vx[r] = 0; vy[r] = 0; vz[r] = 0; vm[r] = 0; }
-    uint32_t ch = p + 1;
-    while (ch < end) {  // children: leaves or depth+1 nodes finished by the previous launch
-        const uint2 mc = meta[ch];
-        const double2 *s2 = reinterpret_cast<const double2 *>(msum4 + 4 * (size_t) ch);
-        const double2 a = s2[0], b = s2[1];
-        const uint32_t rank = (mc.y >> NB_DIGIT_SHIFT) & 7u;
-#pragma unroll
-        for (int r = 0; r < 8; ++r)
-            if (rank == (uint32_t) r) { vx[r] = a.x; vy[r] = a.y; vz[r] = b.x; vm[r] = b.y; }
-        ch = mc.x > ch ? mc.x : end;  // skip links always point forward
-    }
-    // octant code o = 4u + 2r + b  <->  visit rank 4u + 2b + (1-r):  octants 0..7 are ranks 1,3,0,2,5,7,4,6
-    const int rank_of_octant[8] = {1, 3, 0, 2, 5, 7, 4, 6};
-    double sumMasses = 0, cx = 0, cy = 0, cz = 0;
-#pragma unroll
-    for (int o = 0; o < 8; ++o) {
-        const int r = rank_of_octant[o];
-        cx = __dadd_rn(cx, vx[r]);
-        cy = __dadd_rn(cy, vy[r]);
-        cz = __dadd_rn(cz, vz[r]);
-        sumMasses = __dadd_rn(sumMasses, vm[r]);
-    }
     const double half = 0.5 * aabb[6];
     const root_centre origin{aabb[0] + half, aabb[1] + half, aabb[2] + half};
-    store_node(com, comf, msum4, p, cx, cy, cz, sumMasses, origin);
+    for (uint64_t i = (uint64_t) blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (uint64_t) gridDim.x * blockDim.x) {
+        const int d_cur = delta[i];
+        if (depth > d_cur) continue;
+        const int d_prev = i > 0 ? delta[i - 1] : -1;
+        if (depth <= d_prev) continue;
+        const uint32_t p = (uint32_t) (i + base[i] + (uint64_t) (depth - d_prev - 1));
+        const uint32_t end = meta[p].x;
+        // children (leaves, or depth+1 nodes finished by the previous launch), indexed by their visit rank
+        uint32_t child[8];
+#pragma unroll
+        for (int r = 0; r < 8; ++r) child[r] = NB_NONE;
+        uint32_t ch = p + 1;
+        while (ch < end) {
+            const uint2 mc = meta[ch];
+            const uint32_t rank = (mc.y >> NB_DIGIT_SHIFT) & 7u;
+#pragma unroll
+            for (int r = 0; r < 8; ++r)
+                if (rank == (uint32_t) r) child[r] = ch;
+            ch = mc.x > ch ? mc.x : end;  // skip links always point forward
+        }
+        // octant code o = 4u + 2r + b  <->  visit rank 4u + 2b + (1-r):  octants 0..7 are ranks 1,3,0,2,5,7,4,6
+        const int rank_of_octant[8] = {1, 3, 0, 2, 5, 7, 4, 6};
+        double sumMasses = 0, cx = 0, cy = 0, cz = 0;
+#pragma unroll
+        for (int o = 0; o < 8; ++o) {
+            const uint32_t c = child[rank_of_octant[o]];
+            if (c != NB_NONE) {  // an empty octant adds 0.0 in the reference: a no-op
+                const double2 *s2 = reinterpret_cast<const double2 *>(msum4 + 4 * (size_t) c);
+                const double2 a = s2[0], b = s2[1];
+                cx = __dadd_rn(cx, a.x);
+                cy = __dadd_rn(cy, a.y);
+                cz = __dadd_rn(cz, b.x);
+                sumMasses = __dadd_rn(sumMasses, b.y);
+            }
+        }
+        store_node(com, comf, msum4, p, cx, cy, cz, sumMasses, origin);
+        // child table for the group traversal (by visit rank)
+        uint4 *ct = reinterpret_cast<uint4 *>(ctab) + 2 * (size_t) p;
+        ct[0] = make_uint4(child[0], child[1], child[2], child[3]);
+        ct[1] = make_uint4(child[4], child[5], child[6], child[7]);
+    }
 }
 
 }  // namespace
@@ -375,13 +384,14 @@ int nbk_bh_reserve(nb_ctx *ctx) {
     NB_CHECK(nb_alloc(ctx, &b.comf, 4 * cap_nodes));
     NB_CHECK(nb_alloc(ctx, &b.msum, 4 * cap_nodes));
     NB_CHECK(nb_alloc(ctx, &b.meta, cap_nodes));
+    NB_CHECK(nb_alloc(ctx, &b.ctab, 8 * cap_nodes));
     NB_CHECK(nb_alloc(ctx, &b.body_count, cap_nodes));
     const size_t scratch = nbprim::rs_scratch_elems(nb) + nbprim::scan_tiles_for(nb) + 64;
     NB_CHECK(nb_alloc(ctx, &b.hist, scratch));
     NB_CHECK(nb_alloc(ctx, &b.aabb_dev, 8));
     NB_CHECK(nb_alloc(ctx, &b.aabb_partial, 6 * 1024));
     NB_CHECK(nb_alloc(ctx, &b.dev_flags, 8));
-    NB_CHECK(nb_alloc(ctx, &b.stat_totals, 4));
+    NB_CHECK(nb_alloc(ctx, &b.stat_totals, 8));
     NB_CUDA(ctx, cudaMemsetAsync(b.dev_flags, 0, 8 * sizeof(uint32_t), ctx->stream));
     b.cap_bodies = n;
     b.cap_nodes = cap_nodes;
@@ -394,7 +404,7 @@ void nbk_bh_release(nb_ctx *ctx) {
     nb_free(&b.key_hi); nb_free(&b.key_lo); nb_free(&b.key_hi_alt); nb_free(&b.perm); nb_free(&b.perm_alt);
     nb_free(&b.sx); nb_free(&b.sy); nb_free(&b.sz); nb_free(&b.sm); nb_free(&b.delta); nb_free(&b.chain_cnt);
     nb_free(&b.chain_base); nb_free(&b.leaf_node); nb_free(&b.asx); nb_free(&b.asy); nb_free(&b.asz);
-    nb_free(&b.visits); nb_free(&b.com); nb_free(&b.comf); nb_free(&b.msum); nb_free(&b.meta); 
+    nb_free(&b.visits); nb_free(&b.com); nb_free(&b.comf); nb_free(&b.msum); nb_free(&b.meta); nb_free(&b.ctab); 
     nb_free(&b.body_count); nb_free(&b.hist); nb_free(&b.aabb_dev);
     nb_free(&b.aabb_partial); nb_free(&b.dev_flags); nb_free(&b.stat_totals);
     b.cap_bodies = b.cap_nodes = 0;
@@ -464,9 +474,10 @@ int nbk_bh_build(nb_ctx *ctx) {
         com_leaf_kernel<<<g256, 256, 0, ctx->stream>>>(n, b.dev_flags, b.sx, b.sy, b.sz, b.sm, b.leaf_node, b.com, b.comf,
                                                        b.msum, b.aabb_dev);
         NB_LAUNCH_CHECK(ctx);
+        const unsigned level_grid = (unsigned) std::min<uint64_t>(g256, (uint64_t) ctx->sm_count * 32);
         for (int depth = NB_MAX_TREE_DEPTH - 1; depth >= 0; --depth) {
-            com_level_kernel<<<g256, 256, 0, ctx->stream>>>(depth, n, b.dev_flags, b.delta, b.chain_base, b.meta, b.com,
-                                                            b.comf, b.msum, b.aabb_dev);
+            com_level_kernel<<<level_grid, 256, 0, ctx->stream>>>(depth, n, b.dev_flags, b.delta, b.chain_base, b.meta,
+                                                                  b.com, b.comf, b.msum, b.ctab, b.aabb_dev);
             NB_LAUNCH_CHECK(ctx);
         }
     }

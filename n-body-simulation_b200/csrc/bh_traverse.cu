@@ -21,23 +21,42 @@
 
 namespace {
 
-template <bool STATS>
-__global__ void __launch_bounds__(256)
+// scale a positive double by 4^-depth exactly (exponent arithmetic; thresholds are far from the subnormal range)
+__device__ __forceinline__ double scale_pow4(double v, uint32_t depth) {
+    return __hiloint2double(__double2hiint(v) - (int) (depth << 21), __double2loint(v));
+}
+
+// V bit 0: thresholds by exponent arithmetic instead of shared-memory tables; bit 1: prefetch the DFS successor
+__device__ __forceinline__ double scale_pow2(double v, uint32_t depth) {  // v * 2^-depth, exact
+    return __hiloint2double(__double2hiint(v) - (int) (depth << 20), __double2loint(v));
+}
+
+template <bool STATS, int V>
+__global__ void __launch_bounds__(256, (V & 4) ? 5 : 1)
 bh_traverse_kernel(const double4 *__restrict__ com, const uint2 *__restrict__ meta, const uint32_t *__restrict__ flags,
                    uint64_t n_bodies, const double *__restrict__ aabb, const double *__restrict__ sx,
                    const double *__restrict__ sy, const double *__restrict__ sz, uint64_t s_begin, uint64_t s_end,
                    double theta, double eps2, double G, double *__restrict__ asx, double *__restrict__ asy,
                    double *__restrict__ asz, uint32_t *__restrict__ visits, unsigned long long *__restrict__ totals) {
-    __shared__ double t_hi[NB_BH_MAX_LEVELS], t_lo[NB_BH_MAX_LEVELS], t_edge[NB_BH_MAX_LEVELS];
-    for (int t = threadIdx.x; t < NB_BH_MAX_LEVELS; t += blockDim.x) {
-        // edge of a depth-d cell: the root edge halved d times (exact), ParallelOctreeTopDownSubtrees.cpp:256
-        const double e = ldexp(aabb[6], -t);
-        const double ratio = (e / theta) * (e / theta);  // accept  <=>  d2 > (edge/theta)^2  (exact arithmetic)
-        t_edge[t] = e;
-        t_hi[t] = ratio * (1.0 + 1e-12);
-        t_lo[t] = ratio * (1.0 - 1e-12);
+    constexpr bool TABLE_FREE = (V & 1) != 0;
+    constexpr bool PREFETCH = (V & 2) != 0;
+    __shared__ double t_hi[TABLE_FREE ? 1 : NB_BH_MAX_LEVELS], t_lo[TABLE_FREE ? 1 : NB_BH_MAX_LEVELS];
+    const double edge0 = aabb[6];
+    // accept <=> d2 > (edge/theta)^2; a depth-d cell scales the root thresholds by 4^-d exactly (the edge is halved
+    // exactly per level, ParallelOctreeTopDownSubtrees.cpp:256)
+    const double ratio0 = (edge0 / theta) * (edge0 / theta);
+    const bool scalable = ratio0 > 1e-200 && ratio0 < 1e200;  // theta == 0 or absurd boxes: always take the exact branch
+    const double hi0 = scalable ? ratio0 * (1.0 + 1e-12) : __longlong_as_double(0x7ff0000000000000ll);
+    const double lo0 = scalable ? ratio0 * (1.0 - 1e-12) : 0.0;
+    if (!TABLE_FREE) {
+        for (int t = threadIdx.x; t < NB_BH_MAX_LEVELS; t += blockDim.x) {
+            const double e = ldexp(edge0, -t);
+            const double ratio = (e / theta) * (e / theta);
+            t_hi[t] = ratio * (1.0 + 1e-12);
+            t_lo[t] = ratio * (1.0 - 1e-12);
+        }
+        __syncthreads();
     }
-    __syncthreads();
     const uint32_t n_nodes = (uint32_t) n_bodies + flags[1];
     const int lane = threadIdx.x & 31;
     const uint64_t warp_global = ((uint64_t) blockIdx.x * blockDim.x + threadIdx.x) >> 5;
@@ -51,11 +70,20 @@ bh_traverse_kernel(const double4 *__restrict__ com, const uint2 *__restrict__ me
     uint32_t next = (valid && flags[0] == 0) ? 0u : 0xffffffffu;
     uint32_t nvis = 0, nacc = 0;
 
-    while (true) {
-        const uint32_t cur = __reduce_min_sync(0xffffffffu, next);
-        if (cur >= n_nodes) break;
-        const double4 c = com[cur];   // warp-uniform address: one broadcast transaction
-        const uint2 mt = meta[cur];
+    uint32_t cur = __reduce_min_sync(0xffffffffu, next);
+    double4 c = make_double4(0, 0, 0, 0), c_n = c;
+    uint2 mt = make_uint2(0, 0), mt_n = mt;
+    if (PREFETCH && cur < n_nodes) { c = com[cur]; mt = meta[cur]; }
+    while (cur < n_nodes) {
+        if (PREFETCH) {
+            // speculative: the DFS successor is the next cursor whenever a lane opens `cur` or `cur` is a leaf
+            const uint32_t succ = cur + 1 < n_nodes ? cur + 1 : cur;
+            c_n = com[succ];
+            mt_n = meta[succ];
+        } else {
+            c = com[cur];   // warp-uniform address: one broadcast transaction
+            mt = meta[cur];
+        }
         if (next == cur) {
             const double dx = c.x - px, dy = c.y - py, dz = c.z - pz;
             const double d2 = fma(dz, dz, fma(dy, dy, dx * dx));
@@ -66,12 +94,12 @@ bh_traverse_kernel(const double4 *__restrict__ com, const uint2 *__restrict__ me
                 if (STATS) nvis += interact ? 1u : 0u;
             } else {
                 const uint32_t depth = mt.y & NB_PAYLOAD_MASK;
-                bool accept = d2 > t_hi[depth];
-                if (!accept && !(d2 < t_lo[depth])) {
+                bool accept = d2 > (TABLE_FREE ? scale_pow4(hi0, depth) : t_hi[depth]);
+                if (!accept && !(d2 < (TABLE_FREE ? scale_pow4(lo0, depth) : t_lo[depth]))) {
                     // borderline: the oracle's exact expression (BarnesHutAlgorithm.cpp:355-359), no contraction
                     const double d2o = __dadd_rn(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)), __dmul_rn(dz, dz));
                     const double rs = __ddiv_rn(1.0, __dsqrt_rn(d2o));
-                    accept = __dmul_rn(t_edge[depth], rs) < theta;
+                    accept = __dmul_rn(scale_pow2(edge0, depth), rs) < theta;
                 }
                 interact = accept;
                 next = accept ? max(mt.x, cur + 1) : cur + 1;  // skip links always point forward
@@ -92,6 +120,15 @@ bh_traverse_kernel(const double4 *__restrict__ com, const uint2 *__restrict__ me
                 az = fma(dz, s, az);
             }
         }
+        const uint32_t ncur = __reduce_min_sync(0xffffffffu, next);
+        if (PREFETCH) {
+            if (ncur == cur + 1) {
+                c = c_n; mt = mt_n;
+            } else if (ncur < n_nodes) {
+                c = com[ncur]; mt = meta[ncur];
+            }
+        }
+        cur = ncur;
     }
     if (valid) {
         asx[b] = ax * G;
@@ -109,7 +146,6 @@ bh_traverse_kernel(const double4 *__restrict__ com, const uint2 *__restrict__ me
         if (lane == 0) { atomicAdd(&totals[0], v); atomicAdd(&totals[1], a); }
     }
 }
-
 
 // ---------------------------------------------------------------------------------------------------------------------
 // Two-phase variant (default).  The walk above keeps one long dependent chain per node: cursor -> load -> fp64 test ->
@@ -281,6 +317,273 @@ bh_traverse2_kernel(const double4 *__restrict__ com, const float4 *__restrict__ 
     }
 }
 
+
+// ---------------------------------------------------------------------------------------------------------------------
+// Group traversal with exact per-body acceptance (default).
+//
+// A warp owns 32 consecutive bodies of the sorted order and their exact bounding box.  Work items are {node, lane
+// mask} pairs ("this node must be looked at by these bodies") on a per-warp LIFO in shared memory.  Each round pops up
+// to 32 items and classifies them NODE-PARALLEL (one item per lane) against the group box:
+//     nearest point of the box farther than edge/theta  -> every masked body accepts   -> interaction list
+//     farthest point of the box nearer than edge/theta  -> every masked body opens     -> children pushed (same mask)
+//     body leaf                                         -> interaction list (mask minus the body itself)
+//     otherwise ("mixed")                               -> the 32 bodies run the reference's per-body test on that node;
+//                                                          accepting lanes -> interaction list, opening lanes -> children
+// Because every body lies inside the box and the two group thresholds are widened by 1e-9 (>> rounding), a group
+// decision is exactly the decision each masked body's own test (BarnesHutAlgorithm.cpp:355-359) would take, so every
+// body interacts with exactly the reference's node set; only the summation order differs (~1e-16 relative).
+// The interaction list {node, mask} is evaluated branch-free, four entries at a time (see the two-phase kernel).
+// Stack bound: wide pops are only taken while 7*pops fit under CAP-301; otherwise one item is popped per round, which
+// is a plain DFS needing <= 7 slots per level (<= 294 for 42 levels), so the LIFO can never overflow.
+// ---------------------------------------------------------------------------------------------------------------------
+#define NB_G_WARPS 4
+#define NB_G_STACK 1024
+#define NB_G_RESERVE 301
+#define NB_G_ILIST 128
+
+template <bool STATS>
+__global__ void __launch_bounds__(NB_G_WARPS * 32)
+bh_traverse3_kernel(const double4 *__restrict__ com, const uint2 *__restrict__ meta, const uint32_t *__restrict__ ctab,
+                    const uint32_t *__restrict__ flags, uint64_t n_bodies, const double *__restrict__ aabb,
+                    const double *__restrict__ sx, const double *__restrict__ sy, const double *__restrict__ sz,
+                    uint64_t s_begin, uint64_t s_end, double theta, double eps2, double G, double *__restrict__ asx,
+                    double *__restrict__ asy, double *__restrict__ asz, uint32_t *__restrict__ visits,
+                    unsigned long long *__restrict__ totals) {
+    __shared__ double t_hi[NB_BH_MAX_LEVELS], t_lo[NB_BH_MAX_LEVELS], t_edge[NB_BH_MAX_LEVELS];
+    __shared__ double g_hi[NB_BH_MAX_LEVELS], g_lo[NB_BH_MAX_LEVELS];
+    __shared__ uint2 s_stack[NB_G_WARPS][NB_G_STACK];
+    __shared__ uint2 s_ilist[NB_G_WARPS][NB_G_ILIST];
+    for (int t = threadIdx.x; t < NB_BH_MAX_LEVELS; t += blockDim.x) {
+        const double e = ldexp(aabb[6], -t);
+        const double ratio = (e / theta) * (e / theta);
+        t_edge[t] = e;
+        t_hi[t] = ratio * (1.0 + 1e-12);
+        t_lo[t] = ratio * (1.0 - 1e-12);
+        g_hi[t] = ratio * (1.0 + 1e-9);
+        g_lo[t] = ratio * (1.0 - 1e-9);
+    }
+    __syncthreads();
+    const uint32_t n_nodes = (uint32_t) n_bodies + flags[1];
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    const uint32_t lt = (1u << lane) - 1u;
+    const uint64_t warp_global = ((uint64_t) blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const uint64_t wbase = s_begin + warp_global * 32;
+    const uint64_t b = wbase + lane;
+    const bool valid = b < s_end;
+    const uint32_t vmask = __ballot_sync(0xffffffffu, valid);
+    if (vmask == 0 || flags[0] != 0 || n_nodes == 0) {
+        if (valid) { asx[b] = 0; asy[b] = 0; asz[b] = 0; if (STATS) visits[b] = 0; }
+        return;
+    }
+    const uint64_t bsafe = valid ? b : wbase;  // lane 0 is always valid here
+    const double px = sx[bsafe], py = sy[bsafe], pz = sz[bsafe];
+    // exact bounding box of the group
+    double lox = px, loy = py, loz = pz, hix = px, hiy = py, hiz = pz;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        lox = fmin(lox, __shfl_xor_sync(0xffffffffu, lox, o)); hix = fmax(hix, __shfl_xor_sync(0xffffffffu, hix, o));
+        loy = fmin(loy, __shfl_xor_sync(0xffffffffu, loy, o)); hiy = fmax(hiy, __shfl_xor_sync(0xffffffffu, hiy, o));
+        loz = fmin(loz, __shfl_xor_sync(0xffffffffu, loz, o)); hiz = fmax(hiz, __shfl_xor_sync(0xffffffffu, hiz, o));
+    }
+    uint2 *stack = s_stack[wib];
+    uint2 *ilist = s_ilist[wib];
+    double ax = 0, ay = 0, az = 0;
+    uint32_t nvis = 0, nacc = 0;
+    uint32_t size = 0, cnt = 0;
+    if (lane == 0) stack[0] = make_uint2(0u, vmask);
+    size = 1;
+    __syncwarp();
+
+    auto evaluate = [&](uint32_t count) {
+        for (uint32_t k = 0; k < count; k += 4) {
+            double4 r[4];
+            bool on[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const uint2 en = ilist[k + u < count ? k + u : k];
+                r[u] = com[en.x];
+                on[u] = k + u < count && ((en.y >> lane) & 1u);
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const double dx = r[u].x - px, dy = r[u].y - py, dz = r[u].z - pz;
+                const double D = fma(dz, dz, fma(dy, dy, fma(dx, dx, eps2)));
+                const double y0 = nb_rsqrt_seed(D);
+                const double y2 = y0 * y0;
+                const double e = fma(-D, y2, 1.0);
+                const double y3 = y2 * y0;
+                const double q = fma(fma(1.875, e, 1.5), e, 1.0);
+                const double sfac = (y3 * r[u].w) * q;
+                if (on[u]) {
+                    ax = fma(dx, sfac, ax);
+                    ay = fma(dy, sfac, ay);
+                    az = fma(dz, sfac, az);
+                }
+            }
+        }
+    };
+
+    while (size > 0) {
+        if (cnt > NB_G_ILIST - 64) {
+            __syncwarp();
+            evaluate(cnt);
+            __syncwarp();
+            cnt = 0;
+        }
+        // ---- pop: wide while the children are guaranteed to fit under the DFS reserve, else one item (plain DFS)
+        uint32_t k = size < 32u ? size : 32u;
+        const uint32_t wide_room = size + NB_G_RESERVE < NB_G_STACK ? (NB_G_STACK - NB_G_RESERVE - size) / 7u : 0u;
+        if (k > wide_room) k = wide_room > 0 ? wide_room : 1u;
+        const bool have = (uint32_t) lane < k;
+        uint2 item = make_uint2(0u, 0u);
+        if (have) item = stack[size - 1 - lane];
+        size -= k;
+        __syncwarp();
+        // ---- node-parallel classification: 0 none, 1 accept (imask), 2 open, 3 mixed
+        int cls = 0;
+        uint32_t imask = 0, depth = 0;
+        uint4 kid_lo = make_uint4(0xffffffffu, 0xffffffffu, 0xffffffffu, 0xffffffffu), kid_hi = kid_lo;
+        if (have) {
+            // independent loads issued together: one memory latency per round
+            const uint2 mt = meta[item.x];
+            const double4 c = com[item.x];
+            kid_lo = reinterpret_cast<const uint4 *>(ctab)[2 * (size_t) item.x];
+            kid_hi = reinterpret_cast<const uint4 *>(ctab)[2 * (size_t) item.x + 1];
+            if (mt.y & NB_LEAF_FLAG) {
+                const uint64_t sidx = mt.y & NB_PAYLOAD_MASK;  // the leaf's own body never interacts with itself
+                imask = item.y;
+                if (sidx >= wbase && sidx < wbase + 32) imask &= ~(1u << (uint32_t) (sidx - wbase));
+                cls = imask ? 1 : 0;
+            } else {
+                depth = mt.y & NB_PAYLOAD_MASK;
+                const double ex = fmax(0.0, fmax(lox - c.x, c.x - hix));
+                const double ey = fmax(0.0, fmax(loy - c.y, c.y - hiy));
+                const double ez = fmax(0.0, fmax(loz - c.z, c.z - hiz));
+                const double fx = fmax(c.x - lox, hix - c.x);
+                const double fy = fmax(c.y - loy, hiy - c.y);
+                const double fz = fmax(c.z - loz, hiz - c.z);
+                const double dn2 = fma(ez, ez, fma(ey, ey, ex * ex));
+                const double df2 = fma(fz, fz, fma(fy, fy, fx * fx));
+                imask = item.y;
+                cls = dn2 > g_hi[depth] ? 1 : (df2 < g_lo[depth] ? 2 : 3);
+            }
+        }
+        if (STATS) {
+            for (uint32_t j = 0; j < k; ++j) {
+                const uint32_t vm = __shfl_sync(0xffffffffu, imask, j);
+                const int cj = __shfl_sync(0xffffffffu, cls, j);
+                nvis += (vm >> lane) & 1u;
+                if (cj == 1) nacc += (vm >> lane) & 1u;
+            }
+        }
+        if (STATS && lane == 0) {
+            atomicAdd(&totals[2], 1ull);
+            atomicAdd(&totals[3], (unsigned long long) k);
+            atomicAdd(&totals[4], (unsigned long long) __popc(__ballot_sync(0xffffffffu, cls == 3) ));
+        } else if (STATS) { __ballot_sync(0xffffffffu, cls == 3); }
+        // ---- accepted by everybody: append to the interaction list
+        {
+            const uint32_t am = __ballot_sync(0xffffffffu, cls == 1);
+            if (STATS && lane == 0) atomicAdd(&totals[5], (unsigned long long) __popc(am));
+            if (cls == 1) ilist[cnt + __popc(am & lt)] = make_uint2(item.x, imask);
+            cnt += __popc(am);
+        }
+        // ---- opened by everybody: push the children with the same mask
+        {
+            uint32_t kids[8];
+            uint32_t nk = 0;
+            if (cls == 2) {
+                const uint4 c0 = kid_lo, c1 = kid_hi;
+                kids[0] = c0.x; kids[1] = c0.y; kids[2] = c0.z; kids[3] = c0.w;
+                kids[4] = c1.x; kids[5] = c1.y; kids[6] = c1.z; kids[7] = c1.w;
+#pragma unroll
+                for (int r = 0; r < 8; ++r) nk += kids[r] != 0xffffffffu ? 1u : 0u;
+            }
+            // exclusive prefix of nk over the warp
+            uint32_t inc = nk;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const uint32_t t = __shfl_up_sync(0xffffffffu, inc, o);
+                if (lane >= o) inc += t;
+            }
+            const uint32_t total = __shfl_sync(0xffffffffu, inc, 31);
+            if (cls == 2) {
+                uint32_t pos = size + inc - nk;
+#pragma unroll
+                for (int r = 0; r < 8; ++r)
+                    if (kids[r] != 0xffffffffu) stack[pos++] = make_uint2(kids[r], item.y);
+            }
+            size += total;
+        }
+        // ---- mixed: the bodies apply the reference's own test to the node, one node at a time
+        uint32_t mixed = __ballot_sync(0xffffffffu, cls == 3);
+        while (mixed) {
+            // two mixed nodes per trip so their loads and tests overlap
+            const int s0 = __ffs(mixed) - 1;
+            mixed &= mixed - 1;
+            const bool two = mixed != 0;
+            const int s1 = two ? __ffs(mixed) - 1 : s0;
+            if (two) mixed &= mixed - 1;
+            const uint32_t node0 = __shfl_sync(0xffffffffu, item.x, s0), node1 = __shfl_sync(0xffffffffu, item.x, s1);
+            const uint32_t msk0 = __shfl_sync(0xffffffffu, item.y, s0);
+            const uint32_t msk1 = two ? __shfl_sync(0xffffffffu, item.y, s1) : 0u;
+            const uint32_t dep0 = __shfl_sync(0xffffffffu, depth, s0), dep1 = __shfl_sync(0xffffffffu, depth, s1);
+            const double4 c0 = com[node0], c1 = com[node1];
+            uint32_t kid = 0xffffffffu;
+            if (lane < 16) kid = ctab[8 * (size_t) (lane < 8 ? node0 : node1) + (lane & 7)];
+            const double dx0 = c0.x - px, dy0 = c0.y - py, dz0 = c0.z - pz;
+            const double dx1 = c1.x - px, dy1 = c1.y - py, dz1 = c1.z - pz;
+            const double d20 = fma(dz0, dz0, fma(dy0, dy0, dx0 * dx0));
+            const double d21 = fma(dz1, dz1, fma(dy1, dy1, dx1 * dx1));
+            bool acc0 = d20 > t_hi[dep0], acc1 = d21 > t_hi[dep1];
+            if (!acc0 && !(d20 < t_lo[dep0])) {
+                // borderline: the oracle's exact expression (BarnesHutAlgorithm.cpp:355-359), no contraction
+                const double d2o = __dadd_rn(__dadd_rn(__dmul_rn(dx0, dx0), __dmul_rn(dy0, dy0)), __dmul_rn(dz0, dz0));
+                acc0 = __dmul_rn(t_edge[dep0], __ddiv_rn(1.0, __dsqrt_rn(d2o))) < theta;
+            }
+            if (!acc1 && !(d21 < t_lo[dep1])) {
+                const double d2o = __dadd_rn(__dadd_rn(__dmul_rn(dx1, dx1), __dmul_rn(dy1, dy1)), __dmul_rn(dz1, dz1));
+                acc1 = __dmul_rn(t_edge[dep1], __ddiv_rn(1.0, __dsqrt_rn(d2o))) < theta;
+            }
+            const uint32_t am0 = __ballot_sync(0xffffffffu, ((msk0 >> lane) & 1u) && acc0);
+            const uint32_t am1 = __ballot_sync(0xffffffffu, ((msk1 >> lane) & 1u) && acc1);
+            const uint32_t om0 = msk0 & ~am0, om1 = msk1 & ~am1;
+            if (STATS) {
+                nacc += ((am0 >> lane) & 1u) + ((am1 >> lane) & 1u);
+                if (lane == 0) atomicAdd(&totals[5], (unsigned long long) ((am0 != 0) + (am1 != 0)));
+            }
+            if (lane == 0) {
+                if (am0) ilist[cnt] = make_uint2(node0, am0);
+                if (am1) ilist[cnt + (am0 ? 1u : 0u)] = make_uint2(node1, am1);
+            }
+            cnt += (am0 ? 1u : 0u) + (am1 ? 1u : 0u);
+            const uint32_t my_om = lane < 8 ? om0 : om1;
+            const bool push = lane < 16 && kid != 0xffffffffu && my_om != 0;
+            const uint32_t km = __ballot_sync(0xffffffffu, push);
+            if (push) stack[size + __popc(km & lt)] = make_uint2(kid, my_om);
+            size += __popc(km);
+        }
+        __syncwarp();
+    }
+    __syncwarp();
+    evaluate(cnt);
+    if (valid) {
+        asx[b] = ax * G;
+        asy[b] = ay * G;
+        asz[b] = az * G;
+        if (STATS) visits[b] = nvis;
+    }
+    if (STATS) {
+        unsigned long long v = valid ? nvis : 0u, a = valid ? nacc : 0u;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            v += __shfl_xor_sync(0xffffffffu, v, o);
+            a += __shfl_xor_sync(0xffffffffu, a, o);
+        }
+        if (lane == 0) { atomicAdd(&totals[0], v); atomicAdd(&totals[1], a); }
+    }
+}
+
 __global__ void __launch_bounds__(256)
 scatter_accel_kernel(uint64_t n, const uint32_t *__restrict__ perm, const double *__restrict__ asx,
                      const double *__restrict__ asy, const double *__restrict__ asz, double *__restrict__ ax,
@@ -305,7 +608,27 @@ int nbk_bh_accel(nb_ctx *ctx, uint64_t s_begin, uint64_t s_end) {
     const uint64_t count = s_end - s_begin;
     const unsigned grid = (unsigned) ((count + threads - 1) / threads);
     const double4 *com = reinterpret_cast<const double4 *>(b.com);
-    const bool two_phase = ctx->cfg.reserved[1] == 0;  // reserved[1] = 1 selects the single-phase walk (A/B testing)
+    // reserved[1]: 0/1 = warp walk (default), 3 = group traversal, 2 = two-phase walk (both kept for A/B testing; measured
+    // slower on B200 at N = 2^24, theta = 0.5: 94 ms walk vs 112 ms group vs 198 ms two-phase)
+    if (ctx->cfg.reserved[1] == 3) {
+        const unsigned g3 = (unsigned) ((count + NB_G_WARPS * 32 - 1) / (NB_G_WARPS * 32));
+        if (b.stats_enabled) {
+            NB_CUDA(ctx, cudaMemsetAsync(b.stat_totals, 0, 8 * sizeof(unsigned long long), ctx->stream));
+            NB_CUDA(ctx, cudaMemsetAsync(b.visits, 0, ctx->n * sizeof(uint32_t), ctx->stream));
+            bh_traverse3_kernel<true><<<g3, NB_G_WARPS * 32, 0, ctx->stream>>>(com, b.meta, b.ctab, b.dev_flags, ctx->n, b.aabb_dev,
+                                                                             b.sx, b.sy, b.sz, s_begin, s_end, ctx->cfg.theta,
+                                                                             ctx->cfg.epsilon2, ctx->cfg.G, b.asx, b.asy, b.asz,
+                                                                             b.visits, b.stat_totals);
+        } else {
+            bh_traverse3_kernel<false><<<g3, NB_G_WARPS * 32, 0, ctx->stream>>>(com, b.meta, b.ctab, b.dev_flags, ctx->n, b.aabb_dev,
+                                                                              b.sx, b.sy, b.sz, s_begin, s_end, ctx->cfg.theta,
+                                                                              ctx->cfg.epsilon2, ctx->cfg.G, b.asx, b.asy, b.asz,
+                                                                              b.visits, b.stat_totals);
+        }
+        NB_LAUNCH_CHECK(ctx);
+        return NB_OK;
+    }
+    const bool two_phase = ctx->cfg.reserved[1] == 2;
     if (two_phase) {
         const float4 *comf = reinterpret_cast<const float4 *>(b.comf);
         if (b.stats_enabled) {
@@ -324,19 +647,26 @@ int nbk_bh_accel(nb_ctx *ctx, uint64_t s_begin, uint64_t s_end) {
         NB_LAUNCH_CHECK(ctx);
         return NB_OK;
     }
+#define NB_LAUNCH_WALK(ST, VV)                                                                                          \
+    bh_traverse_kernel<ST, VV><<<grid, threads, 0, ctx->stream>>>(com, b.meta, b.dev_flags, ctx->n, b.aabb_dev, b.sx, b.sy, \
+                                                                  b.sz, s_begin, s_end, ctx->cfg.theta, ctx->cfg.epsilon2,  \
+                                                                  ctx->cfg.G, b.asx, b.asy, b.asz, b.visits, b.stat_totals)
     if (b.stats_enabled) {
-        NB_CUDA(ctx, cudaMemsetAsync(b.stat_totals, 0, 2 * sizeof(unsigned long long), ctx->stream));
+        NB_CUDA(ctx, cudaMemsetAsync(b.stat_totals, 0, 8 * sizeof(unsigned long long), ctx->stream));
         NB_CUDA(ctx, cudaMemsetAsync(b.visits, 0, ctx->n * sizeof(uint32_t), ctx->stream));
-        bh_traverse_kernel<true><<<grid, threads, 0, ctx->stream>>>(com, b.meta, b.dev_flags, ctx->n, b.aabb_dev, b.sx,
-                                                                    b.sy, b.sz, s_begin, s_end, ctx->cfg.theta,
-                                                                    ctx->cfg.epsilon2, ctx->cfg.G, b.asx, b.asy, b.asz,
-                                                                    b.visits, b.stat_totals);
+        NB_LAUNCH_WALK(true, 0);
     } else {
-        bh_traverse_kernel<false><<<grid, threads, 0, ctx->stream>>>(com, b.meta, b.dev_flags, ctx->n, b.aabb_dev, b.sx,
-                                                                     b.sy, b.sz, s_begin, s_end, ctx->cfg.theta,
-                                                                     ctx->cfg.epsilon2, ctx->cfg.G, b.asx, b.asy, b.asz,
-                                                                     b.visits, b.stat_totals);
+        switch (ctx->cfg.reserved[3]) {
+            case 1: NB_LAUNCH_WALK(false, 1); break;
+            case 2: NB_LAUNCH_WALK(false, 2); break;
+            case 3: NB_LAUNCH_WALK(false, 3); break;
+            case 5: NB_LAUNCH_WALK(false, 5); break;
+            case 7: NB_LAUNCH_WALK(false, 7); break;
+            case 8: NB_LAUNCH_WALK(false, 0); break;
+            default: NB_LAUNCH_WALK(false, 5); break;  // table-free thresholds, 48 registers (best of the sweep)
+        }
     }
+#undef NB_LAUNCH_WALK
     NB_LAUNCH_CHECK(ctx);
     return NB_OK;
 }

@@ -42,6 +42,7 @@ struct nb_bh_state {
     float *comf = nullptr;                                   // 4 floats per node: COM relative to the root centre, fp32 (walk phase)
     double *msum = nullptr;                                  // 4 doubles per node: {sum m*x, sum m*y, sum m*z, sum m} (reference's massCenters_* / sumOfMasses)
     uint2 *meta = nullptr;
+    uint32_t *ctab = nullptr;                                // 8 child node indices per node, by visit rank (NB_NONE = empty octant)
     uint32_t *body_count = nullptr;
     // sort scratch
     uint32_t *hist = nullptr;

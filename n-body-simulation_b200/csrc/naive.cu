@@ -224,27 +224,27 @@ int nbk_naive_accel(nb_ctx *ctx, uint64_t i_begin, uint64_t i_end) {
         NB_LAUNCH_CHECK(ctx);
     }
     const uint32_t n_tiles = (uint32_t) (n_pad / tile_len);
-    const int ipt = ctx->cfg.reserved[0] > 0 ? ctx->cfg.reserved[0] : 2;  // register blocking (tuning knob)
+    const int ipt = ctx->cfg.reserved[0] > 0 ? ctx->cfg.reserved[0] : 4;  // register blocking (tuning knob)
     const bool precise = ctx->cfg.precise_rsqrt != 0;
     // tuning variants (reserved[2]): {IPT, UNROLL, MINB}; 0 = default
     switch (precise ? ctx->cfg.reserved[2] : 0) {
-        case 1: return launch_naive<1, true, 8, 2>(ctx, n_tiles, tile_len, i_begin, i_end);
-        case 2: return launch_naive<2, true, 2, 2>(ctx, n_tiles, tile_len, i_begin, i_end);
-        case 3: return launch_naive<2, true, 4, 3>(ctx, n_tiles, tile_len, i_begin, i_end);
+        case 1: return launch_naive<6, true, 1, 1>(ctx, n_tiles, tile_len, i_begin, i_end);
+        case 2: return launch_naive<6, true, 2, 1>(ctx, n_tiles, tile_len, i_begin, i_end);
+        case 3: return launch_naive<4, true, 3, 2>(ctx, n_tiles, tile_len, i_begin, i_end);
         case 4: return launch_naive<2, true, 4, 4>(ctx, n_tiles, tile_len, i_begin, i_end);
         case 5: return launch_naive<2, true, 8, 2>(ctx, n_tiles, tile_len, i_begin, i_end);
-        case 6: return launch_naive<4, true, 1, 2>(ctx, n_tiles, tile_len, i_begin, i_end);
+        case 6: return launch_naive<8, true, 1, 1>(ctx, n_tiles, tile_len, i_begin, i_end);
         case 7: return launch_naive<4, true, 2, 2>(ctx, n_tiles, tile_len, i_begin, i_end);
         case 8: return launch_naive<4, true, 2, 3>(ctx, n_tiles, tile_len, i_begin, i_end);
         case 9: return launch_naive<4, true, 4, 1>(ctx, n_tiles, tile_len, i_begin, i_end);
-        case 10: return launch_naive<2, true, 4, 1>(ctx, n_tiles, tile_len, i_begin, i_end);
-        case 11: return launch_naive<1, true, 4, 4>(ctx, n_tiles, tile_len, i_begin, i_end);
+        case 10: return launch_naive<3, true, 4, 2>(ctx, n_tiles, tile_len, i_begin, i_end);
+        case 11: return launch_naive<3, true, 2, 2>(ctx, n_tiles, tile_len, i_begin, i_end);
         default: break;
     }
     if (ipt == 1) return precise ? launch_naive<1, true>(ctx, n_tiles, tile_len, i_begin, i_end)
                                  : launch_naive<1, false>(ctx, n_tiles, tile_len, i_begin, i_end);
-    if (ipt == 4) return precise ? launch_naive<4, true>(ctx, n_tiles, tile_len, i_begin, i_end)
-                                 : launch_naive<4, false>(ctx, n_tiles, tile_len, i_begin, i_end);
+    if (ipt == 4) return precise ? launch_naive<4, true, 2, 2>(ctx, n_tiles, tile_len, i_begin, i_end)   // best of the sweep
+                                 : launch_naive<4, false, 2, 2>(ctx, n_tiles, tile_len, i_begin, i_end);
     return precise ? launch_naive<2, true>(ctx, n_tiles, tile_len, i_begin, i_end)
                    : launch_naive<2, false>(ctx, n_tiles, tile_len, i_begin, i_end);
 }

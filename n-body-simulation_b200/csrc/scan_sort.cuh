@@ -120,8 +120,8 @@ inline int exclusive_scan_u32(nb_ctx *ctx, const uint32_t *in, uint32_t *out, ui
 // ---------------------------------------------------------------------------------------------------------------
 constexpr int RS_THREADS = 256;
 constexpr int RS_WARPS = RS_THREADS / 32;
-constexpr int RS_ITEMS = 16;                      // keys per thread
-constexpr int RS_TILE = RS_THREADS * RS_ITEMS;    // 4096 keys per block
+constexpr int RS_ITEMS = 8;                       // keys per thread
+constexpr int RS_TILE = RS_THREADS * RS_ITEMS;    // 2048 keys per block
 constexpr int RS_BINS = 256;
 
 __global__ void __launch_bounds__(RS_THREADS)
@@ -145,14 +145,16 @@ __global__ void __launch_bounds__(RS_THREADS)
 rs_scatter_kernel(const uint64_t *__restrict__ keys_in, const uint32_t *__restrict__ vals_in, uint64_t n, int shift,
                   uint32_t n_tiles, const uint32_t *__restrict__ hist_scanned, uint64_t *__restrict__ keys_out,
                   uint32_t *__restrict__ vals_out) {
-    __shared__ uint32_t cnt[RS_WARPS][RS_BINS];   // per-warp digit counts, then per-warp exclusive bases
-    __shared__ uint32_t gbase[RS_BINS];
+    __shared__ uint32_t cnt[RS_WARPS][RS_BINS];   // per-warp digit counts, then per-warp exclusive bases inside the tile
+    __shared__ uint32_t gbase[RS_BINS];           // global start of (digit, this tile) minus the digit's start in the tile
+    __shared__ uint64_t skey[RS_TILE];            // tile staged in digit order so the global writes are contiguous runs
+    __shared__ uint32_t sval[RS_TILE];
+    __shared__ uint32_t wsum[RS_WARPS + 1];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     for (int b = threadIdx.x; b < RS_WARPS * RS_BINS; b += RS_THREADS) (&cnt[0][0])[b] = 0;
-    gbase[threadIdx.x] = hist_scanned[(size_t) threadIdx.x * n_tiles + blockIdx.x];
     __syncthreads();
 
-    // warp w owns the contiguous sub-tile [w*512, (w+1)*512) of the tile, processed in 16 rounds of 32 (stable order)
+    // warp w owns the contiguous sub-tile [w*32*ITEMS, (w+1)*32*ITEMS), processed in ITEMS rounds of 32 (stable order)
     const uint64_t wbase = (uint64_t) blockIdx.x * RS_TILE + (uint64_t) warp * (32 * RS_ITEMS);
     uint64_t key[RS_ITEMS];
     uint32_t rank[RS_ITEMS];
@@ -174,16 +176,24 @@ rs_scatter_kernel(const uint64_t *__restrict__ keys_in, const uint32_t *__restri
         rank[k] = prior + __popc(peers & lt);
     }
     __syncthreads();
-    // per-digit exclusive prefix across the warps of the block
+    // thread b owns digit b: exclusive prefix of the digit over the warps, then over the digits of the tile
+    uint32_t digit_total = 0;
     {
-        const int b = threadIdx.x;  // one digit per thread
-        uint32_t run = 0;
+        const int b = threadIdx.x;
 #pragma unroll
         for (int w = 0; w < RS_WARPS; ++w) {
             const uint32_t c = cnt[w][b];
-            cnt[w][b] = run;
-            run += c;
+            cnt[w][b] = digit_total;
+            digit_total += c;
         }
+    }
+    uint32_t tile_total;
+    const uint32_t digit_start = block_excl_scan<RS_THREADS>(digit_total, &tile_total, wsum);
+    {
+        const int b = threadIdx.x;
+#pragma unroll
+        for (int w = 0; w < RS_WARPS; ++w) cnt[w][b] += digit_start;
+        gbase[b] = hist_scanned[(size_t) b * n_tiles + blockIdx.x] - digit_start;
     }
     __syncthreads();
 #pragma unroll
@@ -191,10 +201,20 @@ rs_scatter_kernel(const uint64_t *__restrict__ keys_in, const uint32_t *__restri
         const uint64_t i = wbase + (uint64_t) k * 32 + lane;
         if (i < n) {
             const uint32_t d = (uint32_t) ((key[k] >> shift) & 0xff);
-            const uint64_t pos = (uint64_t) gbase[d] + cnt[warp][d] + rank[k];
-            keys_out[pos] = key[k];
-            vals_out[pos] = IOTA_VALS ? (uint32_t) i : vals_in[i];
+            const uint32_t pos = cnt[warp][d] + rank[k];
+            skey[pos] = key[k];
+            sval[pos] = IOTA_VALS ? (uint32_t) i : vals_in[i];
         }
+    }
+    __syncthreads();
+    const uint64_t tile_base = (uint64_t) blockIdx.x * RS_TILE;
+    const uint32_t tile_count = (uint32_t) (n - tile_base < (uint64_t) RS_TILE ? n - tile_base : (uint64_t) RS_TILE);
+    for (uint32_t pos = threadIdx.x; pos < tile_count; pos += RS_THREADS) {
+        const uint64_t kk = skey[pos];
+        const uint32_t d = (uint32_t) ((kk >> shift) & 0xff);
+        const uint64_t g = (uint64_t) gbase[d] + pos;
+        keys_out[g] = kk;
+        vals_out[g] = sval[pos];
     }
 }
 

@@ -142,8 +142,8 @@ def t_naive_sweep():
     section("naive sweep N=2^20")
     n = 1 << 20
     m, x, y, z, vx, vy, vz = nb.generators.plummer(n, seed=1)
-    names = {0: "ipt2 u4 b2 (default)", 1: "ipt1 u8 b2", 2: "ipt2 u2 b2", 3: "ipt2 u4 b3", 4: "ipt2 u4 b4", 5: "ipt2 u8 b2", 6: "ipt4 u1 b2",
-             7: "ipt4 u2 b2", 8: "ipt4 u2 b3", 9: "ipt4 u4 b1", 10: "ipt2 u4 b1", 11: "ipt1 u4 b4"}
+    names = {0: "ipt2 u4 b2 (default)", 1: "ipt6 u1 b1", 2: "ipt6 u2 b1", 3: "ipt4 u3 b2", 4: "ipt2 u4 b4", 5: "ipt2 u8 b2", 6: "ipt8 u1 b1",
+             7: "ipt4 u2 b2", 8: "ipt4 u2 b3", 9: "ipt4 u4 b1", 10: "ipt3 u4 b2", 11: "ipt3 u2 b2"}
     for var in range(12):
         for bs in (128, 256):
             c = nb.Context(naive_variant=var, block_size=bs)
