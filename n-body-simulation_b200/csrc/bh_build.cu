@@ -272,10 +272,8 @@ emit_kernel(const uint64_t *__restrict__ hi, const uint64_t *__restrict__ lo, co
 // SUM_MASSES != 0 inside one work-group, :263-384): kernel boundaries order the levels.  Every node writes
 //   msum4[n] = {sum m*x, sum m*y, sum m*z, sum m}   (the reference's massCenters_* / sumOfMasses; what parents read)
 //   com[n]   = {sums / mass, mass}                   (the quotient the reference forms per visit, BarnesHutAlgorithm.cpp:351-353)
-//   comf[n]  = fp32(com - root centre)               (walk phase of the traversal)
-struct root_centre { double x, y, z; };
-__device__ __forceinline__ void store_node(double *com, float *comf, double *msum4, uint32_t node, double sx, double sy,
-                                           double sz, double m, const root_centre &o) {
+__device__ __forceinline__ void store_node(double *com, double *msum4, uint32_t node, double sx, double sy, double sz,
+                                           double m) {
     double2 *s2 = reinterpret_cast<double2 *>(msum4 + 4 * (size_t) node);
     s2[0] = make_double2(sx, sy);
     s2[1] = make_double2(sz, m);
@@ -283,30 +281,24 @@ __device__ __forceinline__ void store_node(double *com, float *comf, double *msu
     double2 *c2 = reinterpret_cast<double2 *>(com + 4 * (size_t) node);
     c2[0] = make_double2(cx, cy);
     c2[1] = make_double2(cz, m);
-    reinterpret_cast<float4 *>(comf)[node] = make_float4((float) (cx - o.x), (float) (cy - o.y), (float) (cz - o.z), 0.0f);
 }
 
 __global__ void __launch_bounds__(256)
 com_leaf_kernel(uint64_t n, const uint32_t *__restrict__ flags_in, const double *__restrict__ sx,
                 const double *__restrict__ sy, const double *__restrict__ sz, const double *__restrict__ sm,
-                const uint32_t *__restrict__ leaf_node, double *__restrict__ com, float *__restrict__ comf,
-                double *__restrict__ msum4, const double *__restrict__ aabb) {
+                const uint32_t *__restrict__ leaf_node, double *__restrict__ com, double *__restrict__ msum4) {
     const uint64_t i = (uint64_t) blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n || (flags_in[0] & NB_FLAG_POOL)) return;
-    const double half = 0.5 * aabb[6];
-    const root_centre origin{aabb[0] + half, aabb[1] + half, aabb[2] + half};
     const double m = sm[i];
-    store_node(com, comf, msum4, leaf_node[i], __dmul_rn(sx[i], m), __dmul_rn(sy[i], m), __dmul_rn(sz[i], m), m, origin);
+    store_node(com, msum4, leaf_node[i], __dmul_rn(sx[i], m), __dmul_rn(sy[i], m), __dmul_rn(sz[i], m), m);
 }
 
 __global__ void __launch_bounds__(256)
 com_level_kernel(int depth, uint64_t n, const uint32_t *__restrict__ flags_in, const int32_t *__restrict__ delta,
-                 const uint32_t *__restrict__ base, const uint2 *__restrict__ meta, double *com, float *comf,
-                 double *msum4, uint32_t *__restrict__ ctab, const double *__restrict__ aabb) {
+                 const uint32_t *__restrict__ base, const uint2 *__restrict__ meta, double *com, double *msum4,
+                 uint32_t *__restrict__ ctab /* optional child table for the group traversal */) {
     // flags[2] = deepest leaf = 1 + deepest internal node: nothing to do for the levels below the tree
     if ((uint32_t) depth >= flags_in[2] || (flags_in[0] & NB_FLAG_POOL)) return;
-    const double half = 0.5 * aabb[6];
-    const root_centre origin{aabb[0] + half, aabb[1] + half, aabb[2] + half};
     for (uint64_t i = (uint64_t) blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (uint64_t) gridDim.x * blockDim.x) {
         const int d_cur = delta[i];
         if (depth > d_cur) continue;
@@ -342,11 +334,12 @@ com_level_kernel(int depth, uint64_t n, const uint32_t *__restrict__ flags_in, c
                 sumMasses = __dadd_rn(sumMasses, b.y);
             }
         }
-        store_node(com, comf, msum4, p, cx, cy, cz, sumMasses, origin);
-        // child table for the group traversal (by visit rank)
-        uint4 *ct = reinterpret_cast<uint4 *>(ctab) + 2 * (size_t) p;
-        ct[0] = make_uint4(child[0], child[1], child[2], child[3]);
-        ct[1] = make_uint4(child[4], child[5], child[6], child[7]);
+        store_node(com, msum4, p, cx, cy, cz, sumMasses);
+        if (ctab) {  // child table by visit rank
+            uint4 *ct = reinterpret_cast<uint4 *>(ctab) + 2 * (size_t) p;
+            ct[0] = make_uint4(child[0], child[1], child[2], child[3]);
+            ct[1] = make_uint4(child[4], child[5], child[6], child[7]);
+        }
     }
 }
 
@@ -381,10 +374,8 @@ int nbk_bh_reserve(nb_ctx *ctx) {
     NB_CHECK(nb_alloc(ctx, &b.asz, nb));
     NB_CHECK(nb_alloc(ctx, &b.visits, nb));
     NB_CHECK(nb_alloc(ctx, &b.com, 4 * cap_nodes));
-    NB_CHECK(nb_alloc(ctx, &b.comf, 4 * cap_nodes));
     NB_CHECK(nb_alloc(ctx, &b.msum, 4 * cap_nodes));
     NB_CHECK(nb_alloc(ctx, &b.meta, cap_nodes));
-    NB_CHECK(nb_alloc(ctx, &b.ctab, 8 * cap_nodes));
     NB_CHECK(nb_alloc(ctx, &b.body_count, cap_nodes));
     const size_t scratch = nbprim::rs_scratch_elems(nb) + nbprim::scan_tiles_for(nb) + 64;
     NB_CHECK(nb_alloc(ctx, &b.hist, scratch));
@@ -404,7 +395,7 @@ void nbk_bh_release(nb_ctx *ctx) {
     nb_free(&b.key_hi); nb_free(&b.key_lo); nb_free(&b.key_hi_alt); nb_free(&b.perm); nb_free(&b.perm_alt);
     nb_free(&b.sx); nb_free(&b.sy); nb_free(&b.sz); nb_free(&b.sm); nb_free(&b.delta); nb_free(&b.chain_cnt);
     nb_free(&b.chain_base); nb_free(&b.leaf_node); nb_free(&b.asx); nb_free(&b.asy); nb_free(&b.asz);
-    nb_free(&b.visits); nb_free(&b.com); nb_free(&b.comf); nb_free(&b.msum); nb_free(&b.meta); nb_free(&b.ctab); 
+    nb_free(&b.visits); nb_free(&b.com); nb_free(&b.msum); nb_free(&b.meta); nb_free(&b.ctab); 
     nb_free(&b.body_count); nb_free(&b.hist); nb_free(&b.aabb_dev);
     nb_free(&b.aabb_partial); nb_free(&b.dev_flags); nb_free(&b.stat_totals);
     b.cap_bodies = b.cap_nodes = 0;
@@ -471,13 +462,15 @@ int nbk_bh_build(nb_ctx *ctx) {
     }
     {
         nb_timer_scope t(ctx, NB_T_COM);
-        com_leaf_kernel<<<g256, 256, 0, ctx->stream>>>(n, b.dev_flags, b.sx, b.sy, b.sz, b.sm, b.leaf_node, b.com, b.comf,
-                                                       b.msum, b.aabb_dev);
+        com_leaf_kernel<<<g256, 256, 0, ctx->stream>>>(n, b.dev_flags, b.sx, b.sy, b.sz, b.sm, b.leaf_node, b.com, b.msum);
         NB_LAUNCH_CHECK(ctx);
         const unsigned level_grid = (unsigned) std::min<uint64_t>(g256, (uint64_t) ctx->sm_count * 32);
+        const bool want_ctab = ctx->cfg.reserved[1] == 3;
+        if (want_ctab && !b.ctab) NB_CHECK(nb_alloc(ctx, &b.ctab, 8 * b.cap_nodes));
+        b.ctab_valid = want_ctab;
         for (int depth = NB_MAX_TREE_DEPTH - 1; depth >= 0; --depth) {
             com_level_kernel<<<level_grid, 256, 0, ctx->stream>>>(depth, n, b.dev_flags, b.delta, b.chain_base, b.meta,
-                                                                  b.com, b.comf, b.msum, b.ctab, b.aabb_dev);
+                                                                  b.com, b.msum, want_ctab ? b.ctab : nullptr);
             NB_LAUNCH_CHECK(ctx);
         }
     }

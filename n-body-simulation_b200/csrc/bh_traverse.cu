@@ -11,8 +11,9 @@
 //   * bodies are processed in sorted (Morton / DFS) order so neighbouring lanes share almost all of their lists;
 //   * centre of mass is pre-divided in the COM pass (same IEEE quotient the reference computes per visit);
 //   * acceptance test edge*rsqrt(d2) < theta is decided by two compares of d2 against per-depth thresholds
-//     (edge^2/theta^2 widened by 1e-12); the vanishing band in between is re-evaluated with correctly rounded
-//     sqrt / reciprocal / multiply, i.e. exactly the oracle's expression, so the interaction set is identical;
+//     ((edge/theta)^2 widened by 1e-12, scaled by 4^-depth with exponent arithmetic: no table, no memory access); the
+//     vanishing band in between is re-evaluated with correctly rounded sqrt / reciprocal / multiply, i.e. exactly the
+//     oracle's expression, so the interaction set is identical;
 //   * force: MUFU.RSQ64H seed + cubic Taylor refinement of (d2+eps2)^(-3/2) (see naive.cu).
 // Payload per visited node: 32 B {com xyz, mass} + 8 B {skip, leaf|body / depth} = 40 B.
 #include "common.cuh"
@@ -148,178 +149,7 @@ bh_traverse_kernel(const double4 *__restrict__ com, const uint2 *__restrict__ me
 }
 
 // ---------------------------------------------------------------------------------------------------------------------
-// Two-phase variant (default).  The walk above keeps one long dependent chain per node: cursor -> load -> fp64 test ->
-// rsqrt chain -> accumulate -> next cursor, which leaves the FP64 pipe ~45 % busy (profiles/).  Here the warp
-//   phase 1 (walk):    decides accept/open with an FP32 test on pre-rounded coordinates relative to the root centre
-//                      (FMA pipe, not the FP64 pipe).  The test is conservative: per depth the threshold is widened by a
-//                      rigorous bound of the fp32 error (2.2e-7 * theta * 2^depth + 5e-7, doubled); anything inside the
-//                      band falls back to the fp64 test of the kernel above, including its exact-oracle branch, so the
-//                      interaction set stays identical to the reference's.  Accepted nodes are appended to a per-warp
-//                      list in shared memory as {fp64 record, lane mask}; the next node (cursor+1) is prefetched.
-//   phase 2 (evaluate): when the list is full the warp evaluates it branch-free, two entries at a time, so independent
-//                      rsqrt chains overlap and the FP64 pipe stays fed.  Lanes outside an entry's mask use mass 0.
-// Per-lane summation order is unchanged (list order == visit order).
-// ---------------------------------------------------------------------------------------------------------------------
-#define NB_BH_LIST 32
-
-template <bool STATS>
-__global__ void __launch_bounds__(256)
-bh_traverse2_kernel(const double4 *__restrict__ com, const float4 *__restrict__ comf, const uint2 *__restrict__ meta,
-                    const uint32_t *__restrict__ flags, uint64_t n_bodies, const double *__restrict__ aabb,
-                    const double *__restrict__ sx, const double *__restrict__ sy, const double *__restrict__ sz,
-                    uint64_t s_begin, uint64_t s_end, double theta, double eps2, double G, double *__restrict__ asx,
-                    double *__restrict__ asy, double *__restrict__ asz, uint32_t *__restrict__ visits,
-                    unsigned long long *__restrict__ totals) {
-    __shared__ double t_hi[NB_BH_MAX_LEVELS], t_lo[NB_BH_MAX_LEVELS], t_edge[NB_BH_MAX_LEVELS];
-    __shared__ float f_hi[NB_BH_MAX_LEVELS], f_lo[NB_BH_MAX_LEVELS];
-    __shared__ uint32_t s_node[8][NB_BH_LIST];
-    __shared__ uint32_t s_mask[8][NB_BH_LIST];
-    for (int t = threadIdx.x; t < NB_BH_MAX_LEVELS; t += blockDim.x) {
-        const double e = ldexp(aabb[6], -t);
-        const double ratio = (e / theta) * (e / theta);
-        t_edge[t] = e;
-        t_hi[t] = ratio * (1.0 + 1e-12);
-        t_lo[t] = ratio * (1.0 - 1e-12);
-        // fp32 pre-test: relative error of the fp32 d2 at the acceptance boundary |d| = edge/theta is bounded by
-        // 2*sqrt(3)*2^-24*(R/|d| + 1) + 4*2^-24 <= 2.2e-7*theta*2^depth + 5e-7 (R = root edge); doubled for safety
-        const double marg = 2.0 * (2.2e-7 * fabs(theta) * ldexp(1.0, t) + 5e-7);
-        float hi = __double2float_ru(ratio * (1.0 + marg));
-        float lo = __double2float_rd(ratio * (1.0 - marg));
-        if (!(marg < 0.25) || !(ratio < 1e37) || !(ratio > 1e-37)) { hi = __int_as_float(0x7f800000); lo = 0.0f; }  // fp64 only
-        f_hi[t] = hi;
-        f_lo[t] = lo;
-    }
-    __syncthreads();
-    const uint32_t n_nodes = (uint32_t) n_bodies + flags[1];
-    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
-    const uint64_t warp_global = ((uint64_t) blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    const uint64_t b = s_begin + warp_global * 32 + lane;
-    const bool valid = b < s_end;
-    const uint32_t me = (uint32_t) b;
-    double px = 0, py = 0, pz = 0;
-    if (valid) { px = sx[b]; py = sy[b]; pz = sz[b]; }
-    // fp32 coordinates relative to the centre of the root cube (same reference point as comf)
-    const double hx = aabb[0] + 0.5 * aabb[6], hy = aabb[1] + 0.5 * aabb[6], hz = aabb[2] + 0.5 * aabb[6];
-    const float pfx = (float) (px - hx), pfy = (float) (py - hy), pfz = (float) (pz - hz);
-    double ax = 0, ay = 0, az = 0;
-    uint32_t next = (valid && flags[0] == 0) ? 0u : 0xffffffffu;
-    uint32_t nvis = 0, nacc = 0;
-    uint32_t *my_node = s_node[wib];
-    uint32_t *my_mask = s_mask[wib];
-    uint32_t cnt = 0;
-
-    // phase 2: the list holds {node, lane mask}; records are fetched here, four at a time, so the loads and the four
-    // rsqrt chains are independent and overlap.  Entries past `count` are padded with mask 0 (mass 0 => no contribution).
-    auto evaluate = [&](uint32_t count) {
-        for (uint32_t k = 0; k < count; k += 4) {
-            double4 r[4];
-            double w[4];
-#pragma unroll
-            for (int u = 0; u < 4; ++u) {
-                const uint32_t kk = k + u < count ? k + u : k;
-                r[u] = com[my_node[kk]];
-                const uint32_t mk = k + u < count ? my_mask[kk] : 0u;
-                w[u] = ((mk >> lane) & 1u) ? r[u].w : 0.0;
-            }
-#pragma unroll
-            for (int u = 0; u < 4; ++u) {
-                const double dx = r[u].x - px, dy = r[u].y - py, dz = r[u].z - pz;
-                const double D = fma(dz, dz, fma(dy, dy, fma(dx, dx, eps2)));
-                const double y0 = nb_rsqrt_seed(D);
-                const double y2 = y0 * y0;
-                const double e = fma(-D, y2, 1.0);
-                const double y3 = y2 * y0;
-                const double q = fma(fma(1.875, e, 1.5), e, 1.0);
-                const double sfac = (y3 * w[u]) * q;
-                ax = fma(dx, sfac, ax);
-                ay = fma(dy, sfac, ay);
-                az = fma(dz, sfac, az);
-            }
-        }
-    };
-
-    uint32_t cur = __reduce_min_sync(0xffffffffu, next);
-    float4 cf = make_float4(0, 0, 0, 0);
-    uint2 mt = make_uint2(0, 0);
-    if (cur < n_nodes) { cf = comf[cur]; mt = meta[cur]; }
-    while (cur < n_nodes) {
-        // speculative prefetch of the DFS successor (the most likely next cursor)
-        const uint32_t nxt = cur + 1 < n_nodes ? cur + 1 : cur;
-        const float4 cf_n = comf[nxt];
-        const uint2 mt_n = meta[nxt];
-        bool interact = false;
-        if (next == cur) {
-            if (mt.y & NB_LEAF_FLAG) {
-                interact = (mt.y & NB_PAYLOAD_MASK) != me;
-                next = cur + 1;
-                if (STATS) nvis += interact ? 1u : 0u;
-            } else {
-                const uint32_t depth = mt.y & NB_PAYLOAD_MASK;
-                const float dfx = cf.x - pfx, dfy = cf.y - pfy, dfz = cf.z - pfz;
-                const float d2f = fmaf(dfz, dfz, fmaf(dfy, dfy, dfx * dfx));
-                bool accept = d2f > f_hi[depth];
-                if (!accept && !(d2f < f_lo[depth])) {
-                    // inside the fp32 uncertainty band: fp64 test (and, inside ITS band, the oracle's exact expression)
-                    const double4 c = com[cur];
-                    const double dx = c.x - px, dy = c.y - py, dz = c.z - pz;
-                    const double d2 = fma(dz, dz, fma(dy, dy, dx * dx));
-                    accept = d2 > t_hi[depth];
-                    if (!accept && !(d2 < t_lo[depth])) {
-                        const double d2o = __dadd_rn(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)), __dmul_rn(dz, dz));
-                        const double rs = __ddiv_rn(1.0, __dsqrt_rn(d2o));
-                        accept = __dmul_rn(t_edge[depth], rs) < theta;
-                    }
-                }
-                interact = accept;
-                next = accept ? max(mt.x, cur + 1) : cur + 1;
-                if (STATS) nvis += 1u;
-            }
-        }
-        const uint32_t msk = __ballot_sync(0xffffffffu, interact);
-        if (msk) {
-            if (STATS) nacc += interact ? 1u : 0u;
-            if (lane == 0) {
-                my_node[cnt] = cur;
-                my_mask[cnt] = msk;
-            }
-            ++cnt;
-            if (cnt == NB_BH_LIST) {
-                __syncwarp();
-                evaluate(cnt);
-                __syncwarp();
-                cnt = 0;
-            }
-        }
-        const uint32_t ncur = __reduce_min_sync(0xffffffffu, next);
-        if (ncur == cur + 1) {
-            cf = cf_n; mt = mt_n;
-        } else if (ncur < n_nodes) {
-            cf = comf[ncur]; mt = meta[ncur];
-        }
-        cur = ncur;
-    }
-    __syncwarp();
-    evaluate(cnt);
-    if (valid) {
-        asx[b] = ax * G;
-        asy[b] = ay * G;
-        asz[b] = az * G;
-        if (STATS) visits[b] = nvis;
-    }
-    if (STATS) {
-        unsigned long long v = nvis, a = nacc;
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) {
-            v += __shfl_xor_sync(0xffffffffu, v, o);
-            a += __shfl_xor_sync(0xffffffffu, a, o);
-        }
-        if (lane == 0) { atomicAdd(&totals[0], v); atomicAdd(&totals[1], a); }
-    }
-}
-
-
-// ---------------------------------------------------------------------------------------------------------------------
-// Group traversal with exact per-body acceptance (default).
+// Group traversal with exact per-body acceptance (optional variant, bh_variant = 3).
 //
 // A warp owns 32 consecutive bodies of the sorted order and their exact bounding box.  Work items are {node, lane
 // mask} pairs ("this node must be looked at by these bodies") on a per-warp LIFO in shared memory.  Each round pops up
@@ -332,7 +162,7 @@ bh_traverse2_kernel(const double4 *__restrict__ com, const float4 *__restrict__ 
 // Because every body lies inside the box and the two group thresholds are widened by 1e-9 (>> rounding), a group
 // decision is exactly the decision each masked body's own test (BarnesHutAlgorithm.cpp:355-359) would take, so every
 // body interacts with exactly the reference's node set; only the summation order differs (~1e-16 relative).
-// The interaction list {node, mask} is evaluated branch-free, four entries at a time (see the two-phase kernel).
+// The interaction list {node, mask} is evaluated four entries at a time so independent rsqrt chains overlap.
 // Stack bound: wide pops are only taken while 7*pops fit under CAP-301; otherwise one item is popped per round, which
 // is a plain DFS needing <= 7 slots per level (<= 294 for 42 levels), so the LIFO can never overflow.
 // ---------------------------------------------------------------------------------------------------------------------
@@ -608,9 +438,10 @@ int nbk_bh_accel(nb_ctx *ctx, uint64_t s_begin, uint64_t s_end) {
     const uint64_t count = s_end - s_begin;
     const unsigned grid = (unsigned) ((count + threads - 1) / threads);
     const double4 *com = reinterpret_cast<const double4 *>(b.com);
-    // reserved[1]: 0/1 = warp walk (default), 3 = group traversal, 2 = two-phase walk (both kept for A/B testing; measured
-    // slower on B200 at N = 2^24, theta = 0.5: 94 ms walk vs 112 ms group vs 198 ms two-phase)
+    // reserved[1]: 0 = warp walk (default), 3 = group traversal (kept for A/B testing; measured slower on B200 at
+    // N = 2^24, theta = 0.5: 91 ms walk vs 112 ms group)
     if (ctx->cfg.reserved[1] == 3) {
+        if (!b.ctab_valid) return nb_fail(ctx, NB_ERR_INVALID, "group traversal needs a tree built with bh_variant = 3");
         const unsigned g3 = (unsigned) ((count + NB_G_WARPS * 32 - 1) / (NB_G_WARPS * 32));
         if (b.stats_enabled) {
             NB_CUDA(ctx, cudaMemsetAsync(b.stat_totals, 0, 8 * sizeof(unsigned long long), ctx->stream));
@@ -624,25 +455,6 @@ int nbk_bh_accel(nb_ctx *ctx, uint64_t s_begin, uint64_t s_end) {
                                                                               b.sx, b.sy, b.sz, s_begin, s_end, ctx->cfg.theta,
                                                                               ctx->cfg.epsilon2, ctx->cfg.G, b.asx, b.asy, b.asz,
                                                                               b.visits, b.stat_totals);
-        }
-        NB_LAUNCH_CHECK(ctx);
-        return NB_OK;
-    }
-    const bool two_phase = ctx->cfg.reserved[1] == 2;
-    if (two_phase) {
-        const float4 *comf = reinterpret_cast<const float4 *>(b.comf);
-        if (b.stats_enabled) {
-            NB_CUDA(ctx, cudaMemsetAsync(b.stat_totals, 0, 2 * sizeof(unsigned long long), ctx->stream));
-            NB_CUDA(ctx, cudaMemsetAsync(b.visits, 0, ctx->n * sizeof(uint32_t), ctx->stream));
-            bh_traverse2_kernel<true><<<grid, threads, 0, ctx->stream>>>(com, comf, b.meta, b.dev_flags, ctx->n, b.aabb_dev,
-                                                                         b.sx, b.sy, b.sz, s_begin, s_end, ctx->cfg.theta,
-                                                                         ctx->cfg.epsilon2, ctx->cfg.G, b.asx, b.asy, b.asz,
-                                                                         b.visits, b.stat_totals);
-        } else {
-            bh_traverse2_kernel<false><<<grid, threads, 0, ctx->stream>>>(com, comf, b.meta, b.dev_flags, ctx->n, b.aabb_dev,
-                                                                          b.sx, b.sy, b.sz, s_begin, s_end, ctx->cfg.theta,
-                                                                          ctx->cfg.epsilon2, ctx->cfg.G, b.asx, b.asy, b.asz,
-                                                                          b.visits, b.stat_totals);
         }
         NB_LAUNCH_CHECK(ctx);
         return NB_OK;

@@ -39,7 +39,6 @@ struct nb_bh_state {
     uint32_t *leaf_node = nullptr;                           // node index of the leaf of sorted body i
     // per-node
     double *com = nullptr;                                   // 4 doubles per node
-    float *comf = nullptr;                                   // 4 floats per node: COM relative to the root centre, fp32 (walk phase)
     double *msum = nullptr;                                  // 4 doubles per node: {sum m*x, sum m*y, sum m*z, sum m} (reference's massCenters_* / sumOfMasses)
     uint2 *meta = nullptr;
     uint32_t *ctab = nullptr;                                // 8 child node indices per node, by visit rank (NB_NONE = empty octant)
@@ -61,6 +60,7 @@ struct nb_bh_state {
     uint32_t max_depth = 0;
     double aabb[7] = {0, 0, 0, 0, 0, 0, 0};
     bool built = false;
+    bool ctab_valid = false;
     bool stats_enabled = false;
 };
 

@@ -681,3 +681,39 @@ done:
 }
 
 }  // extern "C"
+
+// ---- analysis helper (not part of the reference): size of the UNION of the node sets visited by a group of bodies ----
+// Used to study warp-cooperative traversal efficiency.  Returns the union size; *sum_visits = sum of per-body visits.
+extern "C" uint64_t orc_bh_group_union(void *h, const double *POS_X, const double *POS_Y, const double *POS_Z, double THETA,
+                                       const int_t *group, int_t gsize, uint64_t *sum_visits) {
+    const Tree &t = *(Tree *) h;
+    const int_t N = t.N;
+    const size_t S = t.S;
+    std::vector<int_t> all;
+    std::vector<int_t> stack;
+    uint64_t visits = 0;
+    for (int_t g = 0; g < gsize; ++g) {
+        int_t i = group[g];
+        stack.clear();
+        stack.push_back(0);
+        while (!stack.empty()) {
+            int_t n = stack.back();
+            stack.pop_back();
+            if (t.mass[n] != 0 && t.bodyOfNode[n] != i) {
+                ++visits;
+                all.push_back(n);
+                double d_x = (t.comx[n] / t.mass[n]) - POS_X[i], d_y = (t.comy[n] / t.mass[n]) - POS_Y[i],
+                       d_z = (t.comz[n] / t.mass[n]) - POS_Z[i];
+                double d = ref_rsqrt(d_x * d_x + d_y * d_y + d_z * d_z);
+                if (!((t.edge[n] * d < THETA) || t.bodyOfNode[n] != N)) {
+                    static const int order[8] = {5, 7, 4, 6, 1, 3, 0, 2};
+                    for (int k = 0; k < 8; ++k) stack.push_back(t.octants[(size_t) order[k] * S + n]);
+                }
+            }
+        }
+    }
+    std::sort(all.begin(), all.end());
+    all.erase(std::unique(all.begin(), all.end()), all.end());
+    *sum_visits = visits;
+    return all.size();
+}

@@ -298,6 +298,24 @@ def test_bh_work_group_size_is_geometry_only(nb, oracle, wg):
     c.close()
 
 
+@pytest.mark.parametrize("variant", [0, 3])
+@pytest.mark.parametrize("theta", [0.3, 0.7])
+def test_bh_traversal_variants_give_identical_interaction_sets(nb, oracle, variant, theta):
+    """bh_variant 0 = warp walk (default), 3 = group traversal with exact per-body acceptance: both must reproduce the
+    reference's per-body node sets (visit / accept counts) and accelerations."""
+    m, x, y, z, *_ = nb.generators.plummer(12345, seed=21)
+    c = nb.Context(device=0, theta=theta, bh_variant=variant)
+    c.set_bodies(m, x, y, z)
+    c.bh_enable_stats(True)
+    c.bh_build(); c.bh_accel()
+    tv, ta, per_body = c.bh_stats(per_body=True)
+    ax, ay, az, st = oracle.Tree(m, x, y, z).accel(theta, stats=True)
+    assert np.array_equal(per_body, st[:, 1].astype(np.uint32))
+    assert (tv, ta) == (int(st[:, 1].sum()), int(st[:, 2].sum()))
+    assert relerr(c.accelerations(), (ax, ay, az)) <= TOL
+    c.close()
+
+
 def test_bh_default_theta_solar_fixture(nb, oracle, ctx, golden_dir):
     m, x, y, z, vx, vy, vz = load_csv(os.path.join(golden_dir, "solar_178.csv"))
     out = ctx.op_barnes_hut_accelerations(m, x, y, z)
