@@ -34,6 +34,9 @@ FLOP_PER_INTERACTION = 21.0          # SURVEY 8d (NaiveAlgorithm.cpp:332-342)
 BH_BYTES_PER_VISIT = 40.0            # com xyz + mass (32 B) + skip/meta (8 B)
 BH_BYTES_PER_BODY = 48.0             # position in, acceleration out
 NAIVE_TILE = 256                     # --block_size used for the benchmark (shared-memory tile length)
+# dram__bytes_read.sum + dram__bytes_write.sum per launch from the `ncu --set full` captures summarised under profiles/
+# (naive: N = 2^20, profiles/naive_accel_r01.txt; Barnes-Hut walk: N = 2^22, profiles/bh_traverse_r01_singlephase.txt)
+NCU_TRAFFIC_BYTES = {("naive", 1 << 20): 90.7392e6 + 25.0391e6, ("bh", 1 << 22): 400.0858e6 + 90.6862e6}
 
 
 def parse_args():
@@ -253,7 +256,7 @@ def measure_bh(nb, torch, dist, args, rank, local_rank, world, dev):
         "visits_per_body": visits / n, "accepts_per_body": accepts / n, "max_depth": int(info.max_depth),
         "internal_nodes_per_body": info.num_internal / n,
         "roofline": {"bound": "hbm", "kernel": "bh_traverse_kernel", "achieved": achieved, "peak": hbm, "unit": "GB/s",
-                     "frac": achieved / hbm, "traffic": None,
+                     "frac": achieved / hbm, "traffic": NCU_TRAFFIC_BYTES.get(("bh", n)) if world == 1 else None,
                      "peak_source": "measured" if "hbm_gbs" in peaks else "fallback",
                      "note": "algorithmic bytes = 40 B x non-empty visits + 48 B x bodies; warp-uniform node loads are "
                              "served from L1/L2, so achieved can exceed the HBM peak"},
@@ -346,7 +349,8 @@ def run_ours(args, rank, local_rank, world):
     k_ms = float(np.mean(kernel_ms))
     achieved_tf = FLOP_PER_INTERACTION * (b1 - b0) * float(n) / (k_ms * 1e-3) / 1e12
     roofline = {"bound": "fp64", "kernel": "naive_accel_kernel", "achieved": achieved_tf, "peak": fp64_peak,
-                "unit": "TFLOP/s", "frac": achieved_tf / fp64_peak if fp64_peak else None, "traffic": None,
+                "unit": "TFLOP/s", "frac": achieved_tf / fp64_peak if fp64_peak else None,
+                "traffic": NCU_TRAFFIC_BYTES.get(("naive", n)) if world == 1 else None,
                 "peak_source": "DFMA-chain microbenchmark in this run (MEASURED_PEAKS.json has no fp64 figure); "
                                "nominal 148 SM x 64 lanes x 2 x 1.965 GHz = 37.2",
                 "algorithmic_flop_per_interaction": FLOP_PER_INTERACTION, "kernel_ms": k_ms,

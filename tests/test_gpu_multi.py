@@ -58,3 +58,26 @@ def test_two_ranks_match_single_gpu(tmp_path):
                        capture_output=True, text=True, timeout=600)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-4000:]
     assert "MULTI_OK" in r.stdout
+
+
+def test_host_executable_two_ranks(tmp_path):
+    """The C++ driver under a torchrun-style launcher: one process per GPU, file rendezvous for the NCCL id, rank 0
+    writes the output; lastState.csv must equal the single-process run byte for byte."""
+    import glob
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    exe = os.path.join(ROOT, "n-body-simulation_b200", "N_Body_Simulation")
+    fixture = os.path.join(ROOT, "tests", "golden", "solar_178.csv")
+    common = ["--file=" + fixture, "--dt=1h", "--t_end=3d", "--vs=1d", "--algorithm=BarnesHut", "--theta=0.5", "--energy=true"]
+    r1 = subprocess.run([exe] + common + ["--vs_dir=" + str(tmp_path / "one")], capture_output=True, text=True, timeout=300)
+    assert r1.returncode == 0, r1.stderr
+    r2 = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2",
+                         "--master-addr", "127.0.0.1", "--master-port", "29544", "--no-python", exe] + common +
+                        ["--vs_dir=" + str(tmp_path / "two")], capture_output=True, text=True, timeout=300)
+    assert r2.returncode == 0, r2.stdout[-1500:] + r2.stderr[-3000:]
+    d1 = glob.glob(str(tmp_path / "one" / "*"))
+    d2 = glob.glob(str(tmp_path / "two" / "*"))
+    assert len(d1) == 1 and len(d2) == 1          # only rank 0 writes
+    for name in ("lastState.csv", "simulation_step3.vtp"):
+        assert open(os.path.join(d1[0], name)).read() == open(os.path.join(d2[0], name)).read(), name
