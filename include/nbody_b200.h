@@ -205,8 +205,9 @@ int nb_event_elapsed_ms(nb_ctx *ctx, int slot_begin, int slot_end, double *ms); 
 int nb_measure_fp64_peak(nb_ctx *ctx, double *tflops);
 /* number of kernel launches issued by this context so far (bench.py's gpu_launches).                     */
 uint64_t nb_launch_count(const nb_ctx *ctx);
-/* raw device pointers (x,y,z,vx,vy,vz,ax,ay,az,mass) for zero-copy wrappers; valid until the next
- * nb_set_bodies with a larger N.                                                                          */
+/* raw device pointers (x,y,z,vx,vy,vz,ax,ay,az,mass) for zero-copy wrappers.  The arrays are in STORAGE order: body-id
+ * order until the first nb_bh_build, the sorted (Morton) order of the latest build afterwards, and every build swaps
+ * the buffers -- re-query after nb_bh_build / nb_set_bodies.                                              */
 int nb_device_pointers(nb_ctx *ctx, void *ptrs[10]);
 
 #ifdef __cplusplus

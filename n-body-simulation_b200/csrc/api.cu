@@ -105,6 +105,8 @@ void nb_destroy(nb_ctx *ctx) {
     nb_free(&ctx->vx); nb_free(&ctx->vy); nb_free(&ctx->vz);
     nb_free(&ctx->ax); nb_free(&ctx->ay); nb_free(&ctx->az);
     nb_free(&ctx->anorm); nb_free(&ctx->src); nb_free(&ctx->e_partial);
+    for (int k = 0; k < 10; ++k) nb_free(&ctx->alt[k]);
+    nb_free(&ctx->id); nb_free(&ctx->id_alt);
     if (ctx->h_pinned) cudaFreeHost(ctx->h_pinned);
     for (int i = 0; i < 2 * NB_T_COUNT; ++i) cudaEventDestroy(ctx->ev[i]);
     for (int i = 0; i < 8; ++i) cudaEventDestroy(ctx->user_ev[i]);
@@ -153,6 +155,9 @@ static int ensure_capacity(nb_ctx *ctx, uint64_t n) {
     NB_CHECK(nb_alloc(ctx, &ctx->ay, need));
     NB_CHECK(nb_alloc(ctx, &ctx->az, need));
     NB_CHECK(nb_alloc(ctx, &ctx->anorm, need));
+    for (int k = 0; k < 10; ++k) NB_CHECK(nb_alloc(ctx, &ctx->alt[k], need));
+    NB_CHECK(nb_alloc(ctx, &ctx->id, need));
+    NB_CHECK(nb_alloc(ctx, &ctx->id_alt, need));
     NB_CHECK(nb_alloc(ctx, &ctx->e_partial, 2 * need + 8 + 2048));
     ctx->cap = need;
     return NB_OK;
@@ -177,6 +182,7 @@ int nb_set_bodies(nb_ctx *ctx, uint64_t n, const double *mass, const double *x, 
     NB_CHECK(ensure_capacity(ctx, n));
     ctx->n = n;
     ctx->bh.built = false;
+    ctx->identity_order = true;  // storage order == body-id order until the next Barnes-Hut build
     NB_CHECK(h2d(ctx, ctx->m, mass, n));
     NB_CHECK(h2d(ctx, ctx->x, x, n));
     NB_CHECK(h2d(ctx, ctx->y, y, n));
@@ -201,9 +207,19 @@ int nb_set_bodies(nb_ctx *ctx, uint64_t n, const double *mass, const double *x, 
 int nb_set_positions(nb_ctx *ctx, const double *x, const double *y, const double *z) {
     if (!ctx || !ctx->n) return nb_fail(ctx, NB_ERR_INVALID, "nb_set_positions: no bodies");
     NB_CUDA(ctx, cudaSetDevice(ctx->device));
-    NB_CHECK(h2d(ctx, ctx->x, x, ctx->n));
-    NB_CHECK(h2d(ctx, ctx->y, y, ctx->n));
-    NB_CHECK(h2d(ctx, ctx->z, z, ctx->n));
+    if (!x || !y || !z) return nb_fail(ctx, NB_ERR_INVALID, "nb_set_positions: null array");
+    if (ctx->identity_order) {
+        NB_CHECK(h2d(ctx, ctx->x, x, ctx->n));
+        NB_CHECK(h2d(ctx, ctx->y, y, ctx->n));
+        NB_CHECK(h2d(ctx, ctx->z, z, ctx->n));
+    } else {  // host arrays are in body-id order, the device state in storage order
+        NB_CHECK(h2d(ctx, ctx->alt[1], x, ctx->n));
+        NB_CHECK(h2d(ctx, ctx->alt[2], y, ctx->n));
+        NB_CHECK(h2d(ctx, ctx->alt[3], z, ctx->n));
+        const double *src[3] = {ctx->alt[1], ctx->alt[2], ctx->alt[3]};
+        double *dst[3] = {ctx->x, ctx->y, ctx->z};
+        NB_CHECK(nbk_permute_in(ctx, 3, src, dst));
+    }
     ctx->bh.built = false;
     NB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     return NB_OK;
@@ -234,8 +250,7 @@ int nb_bh_accel(nb_ctx *ctx) {
     uint64_t b = 0, e = ctx->n;
     nb_slice_bounds(ctx->n, ctx->world, ctx->rank, &b, &e);
     NB_CHECK(nbk_bh_accel(ctx, b, e));
-    NB_CHECK(nbk_comm_allgather_accel(ctx, ctx->bh.asx, ctx->bh.asy, ctx->bh.asz, ctx->n));
-    NB_CHECK(nbk_bh_scatter_accel(ctx));
+    NB_CHECK(nbk_comm_allgather_accel(ctx, ctx->ax, ctx->ay, ctx->az, ctx->n));
     return NB_OK;
 }
 
@@ -289,30 +304,51 @@ int nb_energy(nb_ctx *ctx, double out[4]) {
 }
 
 // ---- read-back ----------------------------------------------------------------------------------------------------------
-int nb_get_positions(nb_ctx *ctx, double *x, double *y, double *z) {
+// Host arrays are always in body-id order.  After a Barnes-Hut build the device state is in storage (sorted) order:
+// the requested arrays are un-permuted on the device into the idle ping-pong buffers and copied from there.
+static int read_back(nb_ctx *ctx, int count, const double *const *dev, double *const *host) {
     if (!ctx || !ctx->n) return nb_fail(ctx, NB_ERR_INVALID, "no bodies");
     NB_CUDA(ctx, cudaSetDevice(ctx->device));
-    NB_CHECK(d2h(ctx, x, ctx->x, ctx->n)); NB_CHECK(d2h(ctx, y, ctx->y, ctx->n)); NB_CHECK(d2h(ctx, z, ctx->z, ctx->n));
+    if (ctx->identity_order) {
+        for (int k = 0; k < count; ++k) NB_CHECK(d2h(ctx, host[k], dev[k], ctx->n));
+    } else {
+        const double *src[10];
+        double *dst[10];
+        int m = 0;
+        for (int k = 0; k < count; ++k)
+            if (host[k]) { src[m] = dev[k]; dst[m] = ctx->alt[m]; ++m; }
+        if (m) NB_CHECK(nbk_unpermute(ctx, m, src, dst));
+        m = 0;
+        for (int k = 0; k < count; ++k)
+            if (host[k]) { NB_CHECK(d2h(ctx, host[k], ctx->alt[m], ctx->n)); ++m; }
+    }
     return nb_synchronize(ctx);
+}
+int nb_get_positions(nb_ctx *ctx, double *x, double *y, double *z) {
+    if (!ctx) return NB_ERR_INVALID;
+    const double *dev[3] = {ctx->x, ctx->y, ctx->z};
+    double *host[3] = {x, y, z};
+    return read_back(ctx, 3, dev, host);
 }
 int nb_get_velocities(nb_ctx *ctx, double *vx, double *vy, double *vz) {
-    if (!ctx || !ctx->n) return nb_fail(ctx, NB_ERR_INVALID, "no bodies");
-    NB_CUDA(ctx, cudaSetDevice(ctx->device));
-    NB_CHECK(d2h(ctx, vx, ctx->vx, ctx->n)); NB_CHECK(d2h(ctx, vy, ctx->vy, ctx->n)); NB_CHECK(d2h(ctx, vz, ctx->vz, ctx->n));
-    return nb_synchronize(ctx);
+    if (!ctx) return NB_ERR_INVALID;
+    const double *dev[3] = {ctx->vx, ctx->vy, ctx->vz};
+    double *host[3] = {vx, vy, vz};
+    return read_back(ctx, 3, dev, host);
 }
 int nb_get_accelerations(nb_ctx *ctx, double *ax, double *ay, double *az) {
-    if (!ctx || !ctx->n) return nb_fail(ctx, NB_ERR_INVALID, "no bodies");
-    NB_CUDA(ctx, cudaSetDevice(ctx->device));
-    NB_CHECK(d2h(ctx, ax, ctx->ax, ctx->n)); NB_CHECK(d2h(ctx, ay, ctx->ay, ctx->n)); NB_CHECK(d2h(ctx, az, ctx->az, ctx->n));
-    return nb_synchronize(ctx);
+    if (!ctx) return NB_ERR_INVALID;
+    const double *dev[3] = {ctx->ax, ctx->ay, ctx->az};
+    double *host[3] = {ax, ay, az};
+    return read_back(ctx, 3, dev, host);
 }
 int nb_get_acceleration_norms(nb_ctx *ctx, double *anorm) {
     if (!ctx || !ctx->n || !anorm) return nb_fail(ctx, NB_ERR_INVALID, "no bodies");
     NB_CUDA(ctx, cudaSetDevice(ctx->device));
     NB_CHECK(nbk_accel_norm(ctx));
-    NB_CHECK(d2h(ctx, anorm, ctx->anorm, ctx->n));
-    return nb_synchronize(ctx);
+    const double *dev[1] = {ctx->anorm};
+    double *host[1] = {anorm};
+    return read_back(ctx, 1, dev, host);
 }
 
 int nb_device_pointers(nb_ctx *ctx, void *p[10]) {
@@ -329,6 +365,7 @@ static int upload_for_op(nb_ctx *ctx, uint64_t n, const double *mass, const doub
     NB_CHECK(ensure_capacity(ctx, n));
     ctx->n = n;
     ctx->bh.built = false;
+    ctx->identity_order = true;
     NB_CHECK(h2d(ctx, ctx->m, mass, n));
     NB_CHECK(h2d(ctx, ctx->x, x, n));
     NB_CHECK(h2d(ctx, ctx->y, y, n));
@@ -467,10 +504,10 @@ int nb_bh_get_stats(nb_ctx *ctx, uint64_t *total_visits, uint64_t *total_accepts
     if (total_accepts) *total_accepts = t[1];
     if (visits_per_body) {
         // device counters are in sorted order; return them by body id
-        std::vector<uint32_t> v(ctx->n), perm(ctx->n);
+        std::vector<uint32_t> v(ctx->n), ids(ctx->n);
         NB_CUDA(ctx, cudaMemcpy(v.data(), ctx->bh.visits, ctx->n * sizeof(uint32_t), cudaMemcpyDeviceToHost));
-        NB_CUDA(ctx, cudaMemcpy(perm.data(), ctx->bh.perm, ctx->n * sizeof(uint32_t), cudaMemcpyDeviceToHost));
-        for (uint64_t s = 0; s < ctx->n; ++s) visits_per_body[perm[s]] = v[s];
+        NB_CUDA(ctx, cudaMemcpy(ids.data(), ctx->id, ctx->n * sizeof(uint32_t), cudaMemcpyDeviceToHost));
+        for (uint64_t s = 0; s < ctx->n; ++s) visits_per_body[ids[s]] = v[s];
     }
     return NB_OK;
 }
@@ -496,7 +533,7 @@ int fetch_tree(nb_ctx *ctx, HostTree &t) {
     NB_CUDA(ctx, cudaMemcpy(t.com.data(), b.com, 4 * t.M * sizeof(double), cudaMemcpyDeviceToHost));
     NB_CUDA(ctx, cudaMemcpy(t.msum.data(), b.msum, 4 * t.M * sizeof(double), cudaMemcpyDeviceToHost));
     NB_CUDA(ctx, cudaMemcpy(t.body_count.data(), b.body_count, t.M * sizeof(uint32_t), cudaMemcpyDeviceToHost));
-    NB_CUDA(ctx, cudaMemcpy(t.perm.data(), b.perm, t.n * sizeof(uint32_t), cudaMemcpyDeviceToHost));
+    NB_CUDA(ctx, cudaMemcpy(t.perm.data(), ctx->id, t.n * sizeof(uint32_t), cudaMemcpyDeviceToHost));  // slot -> body id
     NB_CUDA(ctx, cudaMemcpy(t.aabb, b.aabb_dev, 7 * sizeof(double), cudaMemcpyDeviceToHost));
     return NB_OK;
 }

@@ -14,7 +14,9 @@
 //   1. every body descends the cube arithmetically (exactly the reference's fp64 compares) and records its path as
 //      2 x 63-bit keys, 3 bits per level, 42 levels.  The digit is the octant's VISIT RANK 4u+2b+(1-r) in the
 //      reference's traversal order [2,0,3,1,6,4,7,5] (BarnesHutAlgorithm.cpp:370-385), so sorted order == DFS order.
-//   2. stable LSD radix sort of (key_hi, body) (scan_sort.cuh); rare equal-key_hi runs are ordered by key_lo.
+//   2. stable LSD radix sort of (key_hi, slot) (scan_sort.cuh); rare equal-key_hi runs are ordered by key_lo; then the
+//      whole body state (m, x, v, a, id) is physically permuted into the sorted order, so everything downstream streams
+//      and the next step's permutation is a near-identity map (bodies move little per step).
 //   3. delta[i] = common-prefix digits of sorted neighbours.  Body i is the FIRST body of the internal cells of depth
 //      delta[i-1]+1 .. delta[i]; an exclusive scan of those counts gives every node its index in a DFS pre-order
 //      array (internal chain of body i, then leaf i).  Empty leaves are implied, never materialised.
@@ -169,17 +171,38 @@ fix_ties_kernel(const uint64_t *__restrict__ hi_sorted, const uint64_t *__restri
     }
 }
 
-// ---- 3. gather into sorted order ---------------------------------------------------------------------------------------
+// ---- 3. physical reorder of the whole state into sorted order ----------------------------------------------------------------
+struct reorder_args {
+    const double *src[10];
+    double *dst[10];
+};
 __global__ void __launch_bounds__(256)
-gather_kernel(const uint32_t *__restrict__ perm, uint64_t n, const double *__restrict__ x, const double *__restrict__ y,
-              const double *__restrict__ z, const double *__restrict__ m, const uint64_t *__restrict__ key_lo,
-              double *__restrict__ sx, double *__restrict__ sy, double *__restrict__ sz, double *__restrict__ sm,
-              uint64_t *__restrict__ lo_sorted) {
+reorder_kernel(const uint32_t *__restrict__ perm, uint64_t n, reorder_args a, const uint32_t *__restrict__ id_in,
+               uint32_t *__restrict__ id_out, int identity, const uint64_t *__restrict__ key_lo,
+               uint64_t *__restrict__ lo_sorted) {
     const uint64_t i = (uint64_t) blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
-    const uint32_t b = perm[i];
-    sx[i] = x[b]; sy[i] = y[b]; sz[i] = z[b]; sm[i] = m[b];
-    lo_sorted[i] = key_lo[b];
+    const uint32_t p = perm[i];
+#pragma unroll
+    for (int k = 0; k < 10; ++k) a.dst[k][i] = a.src[k][p];
+    id_out[i] = identity ? p : id_in[p];
+    lo_sorted[i] = key_lo[p];
+}
+
+// read-back / upload helpers between storage order and body-id order
+__global__ void __launch_bounds__(256)
+unpermute_kernel(uint64_t n, const uint32_t *__restrict__ id, int count, reorder_args a) {
+    const uint64_t s = (uint64_t) blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= n) return;
+    const uint32_t b = id[s];
+    for (int k = 0; k < count; ++k) a.dst[k][b] = a.src[k][s];
+}
+__global__ void __launch_bounds__(256)
+permute_in_kernel(uint64_t n, const uint32_t *__restrict__ id, int count, reorder_args a) {
+    const uint64_t s = (uint64_t) blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= n) return;
+    const uint32_t b = id[s];
+    for (int k = 0; k < count; ++k) a.dst[k][s] = a.src[k][b];
 }
 
 __device__ __forceinline__ int common_digits(uint64_t hi_a, uint64_t lo_a, uint64_t hi_b, uint64_t lo_b) {
@@ -284,13 +307,13 @@ __device__ __forceinline__ void store_node(double *com, double *msum4, uint32_t 
 }
 
 __global__ void __launch_bounds__(256)
-com_leaf_kernel(uint64_t n, const uint32_t *__restrict__ flags_in, const double *__restrict__ sx,
-                const double *__restrict__ sy, const double *__restrict__ sz, const double *__restrict__ sm,
+com_leaf_kernel(uint64_t n, const uint32_t *__restrict__ flags_in, const double *__restrict__ px,
+                const double *__restrict__ py, const double *__restrict__ pz, const double *__restrict__ pm,
                 const uint32_t *__restrict__ leaf_node, double *__restrict__ com, double *__restrict__ msum4) {
     const uint64_t i = (uint64_t) blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n || (flags_in[0] & NB_FLAG_POOL)) return;
-    const double m = sm[i];
-    store_node(com, msum4, leaf_node[i], __dmul_rn(sx[i], m), __dmul_rn(sy[i], m), __dmul_rn(sz[i], m), m);
+    const double m = pm[i];
+    store_node(com, msum4, leaf_node[i], __dmul_rn(px[i], m), __dmul_rn(py[i], m), __dmul_rn(pz[i], m), m);
 }
 
 __global__ void __launch_bounds__(256)
@@ -361,17 +384,10 @@ int nbk_bh_reserve(nb_ctx *ctx) {
     NB_CHECK(nb_alloc(ctx, &b.key_hi_alt, nb));
     NB_CHECK(nb_alloc(ctx, &b.perm, nb));
     NB_CHECK(nb_alloc(ctx, &b.perm_alt, nb));
-    NB_CHECK(nb_alloc(ctx, &b.sx, nb));
-    NB_CHECK(nb_alloc(ctx, &b.sy, nb));
-    NB_CHECK(nb_alloc(ctx, &b.sz, nb));
-    NB_CHECK(nb_alloc(ctx, &b.sm, nb));
     NB_CHECK(nb_alloc(ctx, &b.delta, nb));
     NB_CHECK(nb_alloc(ctx, &b.chain_cnt, nb));
     NB_CHECK(nb_alloc(ctx, &b.chain_base, nb));
     NB_CHECK(nb_alloc(ctx, &b.leaf_node, nb));
-    NB_CHECK(nb_alloc(ctx, &b.asx, nb));
-    NB_CHECK(nb_alloc(ctx, &b.asy, nb));
-    NB_CHECK(nb_alloc(ctx, &b.asz, nb));
     NB_CHECK(nb_alloc(ctx, &b.visits, nb));
     NB_CHECK(nb_alloc(ctx, &b.com, 4 * cap_nodes));
     NB_CHECK(nb_alloc(ctx, &b.msum, 4 * cap_nodes));
@@ -393,8 +409,8 @@ int nbk_bh_reserve(nb_ctx *ctx) {
 void nbk_bh_release(nb_ctx *ctx) {
     nb_bh_state &b = ctx->bh;
     nb_free(&b.key_hi); nb_free(&b.key_lo); nb_free(&b.key_hi_alt); nb_free(&b.perm); nb_free(&b.perm_alt);
-    nb_free(&b.sx); nb_free(&b.sy); nb_free(&b.sz); nb_free(&b.sm); nb_free(&b.delta); nb_free(&b.chain_cnt);
-    nb_free(&b.chain_base); nb_free(&b.leaf_node); nb_free(&b.asx); nb_free(&b.asy); nb_free(&b.asz);
+    nb_free(&b.delta); nb_free(&b.chain_cnt);
+    nb_free(&b.chain_base); nb_free(&b.leaf_node); 
     nb_free(&b.visits); nb_free(&b.com); nb_free(&b.msum); nb_free(&b.meta); nb_free(&b.ctab); 
     nb_free(&b.body_count); nb_free(&b.hist); nb_free(&b.aabb_dev);
     nb_free(&b.aabb_partial); nb_free(&b.dev_flags); nb_free(&b.stat_totals);
@@ -444,10 +460,18 @@ int nbk_bh_build(nb_ctx *ctx) {
             uint64_t *tk = b.key_hi; b.key_hi = b.key_hi_alt; b.key_hi_alt = tk;
             uint32_t *tp = b.perm; b.perm = b.perm_alt; b.perm_alt = tp;
         }
-        // sorted positions / masses / key_lo (key_hi_alt receives the sorted key_lo)
-        gather_kernel<<<g256, 256, 0, ctx->stream>>>(b.perm, n, ctx->x, ctx->y, ctx->z, ctx->m, b.key_lo, b.sx, b.sy,
-                                                     b.sz, b.sm, b.key_hi_alt);
-        NB_LAUNCH_CHECK(ctx);
+        // move the whole state (and key_lo -> key_hi_alt) into sorted order; the arrays swap roles with their partners
+        {
+            double **cur[10] = {&ctx->m, &ctx->x, &ctx->y, &ctx->z, &ctx->vx, &ctx->vy, &ctx->vz, &ctx->ax, &ctx->ay, &ctx->az};
+            reorder_args ra;
+            for (int k = 0; k < 10; ++k) { ra.src[k] = *cur[k]; ra.dst[k] = ctx->alt[k]; }
+            reorder_kernel<<<g256, 256, 0, ctx->stream>>>(b.perm, n, ra, ctx->id, ctx->id_alt, ctx->identity_order ? 1 : 0,
+                                                          b.key_lo, b.key_hi_alt);
+            NB_LAUNCH_CHECK(ctx);
+            for (int k = 0; k < 10; ++k) { double *t = *cur[k]; *cur[k] = ctx->alt[k]; ctx->alt[k] = t; }
+            uint32_t *ti = ctx->id; ctx->id = ctx->id_alt; ctx->id_alt = ti;
+            ctx->identity_order = false;
+        }
     }
     const uint64_t *hi = b.key_hi, *lo = b.key_hi_alt;
     {
@@ -462,7 +486,7 @@ int nbk_bh_build(nb_ctx *ctx) {
     }
     {
         nb_timer_scope t(ctx, NB_T_COM);
-        com_leaf_kernel<<<g256, 256, 0, ctx->stream>>>(n, b.dev_flags, b.sx, b.sy, b.sz, b.sm, b.leaf_node, b.com, b.msum);
+        com_leaf_kernel<<<g256, 256, 0, ctx->stream>>>(n, b.dev_flags, ctx->x, ctx->y, ctx->z, ctx->m, b.leaf_node, b.com, b.msum);
         NB_LAUNCH_CHECK(ctx);
         const unsigned level_grid = (unsigned) std::min<uint64_t>(g256, (uint64_t) ctx->sm_count * 32);
         const bool want_ctab = ctx->cfg.reserved[1] == 3;
@@ -475,5 +499,21 @@ int nbk_bh_build(nb_ctx *ctx) {
         }
     }
     b.built = true;
+    return NB_OK;
+}
+
+int nbk_unpermute(nb_ctx *ctx, int count, const double *const *src, double *const *dst) {
+    reorder_args ra = {};
+    for (int k = 0; k < count; ++k) { ra.src[k] = src[k]; ra.dst[k] = dst[k]; }
+    unpermute_kernel<<<(unsigned) ((ctx->n + 255) / 256), 256, 0, ctx->stream>>>(ctx->n, ctx->id, count, ra);
+    NB_LAUNCH_CHECK(ctx);
+    return NB_OK;
+}
+
+int nbk_permute_in(nb_ctx *ctx, int count, const double *const *src, double *const *dst) {
+    reorder_args ra = {};
+    for (int k = 0; k < count; ++k) { ra.src[k] = src[k]; ra.dst[k] = dst[k]; }
+    permute_in_kernel<<<(unsigned) ((ctx->n + 255) / 256), 256, 0, ctx->stream>>>(ctx->n, ctx->id, count, ra);
+    NB_LAUNCH_CHECK(ctx);
     return NB_OK;
 }

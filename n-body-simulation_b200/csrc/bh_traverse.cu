@@ -414,19 +414,9 @@ bh_traverse3_kernel(const double4 *__restrict__ com, const uint2 *__restrict__ m
     }
 }
 
-__global__ void __launch_bounds__(256)
-scatter_accel_kernel(uint64_t n, const uint32_t *__restrict__ perm, const double *__restrict__ asx,
-                     const double *__restrict__ asy, const double *__restrict__ asz, double *__restrict__ ax,
-                     double *__restrict__ ay, double *__restrict__ az) {
-    const uint64_t s = (uint64_t) blockIdx.x * blockDim.x + threadIdx.x;
-    if (s >= n) return;
-    const uint32_t b = perm[s];
-    ax[b] = asx[s]; ay[b] = asy[s]; az[b] = asz[s];
-}
-
 }  // namespace
 
-// Accelerations of the sorted bodies [s_begin, s_end) into the sorted-order arrays asx/asy/asz.
+// Accelerations of the bodies in storage slots [s_begin, s_end) (storage order == sorted order after nb_bh_build).
 int nbk_bh_accel(nb_ctx *ctx, uint64_t s_begin, uint64_t s_end) {
     nb_bh_state &b = ctx->bh;
     if (!b.built) return nb_fail(ctx, NB_ERR_INVALID, "nb_bh_accel: call nb_bh_build first");
@@ -447,22 +437,22 @@ int nbk_bh_accel(nb_ctx *ctx, uint64_t s_begin, uint64_t s_end) {
             NB_CUDA(ctx, cudaMemsetAsync(b.stat_totals, 0, 8 * sizeof(unsigned long long), ctx->stream));
             NB_CUDA(ctx, cudaMemsetAsync(b.visits, 0, ctx->n * sizeof(uint32_t), ctx->stream));
             bh_traverse3_kernel<true><<<g3, NB_G_WARPS * 32, 0, ctx->stream>>>(com, b.meta, b.ctab, b.dev_flags, ctx->n, b.aabb_dev,
-                                                                             b.sx, b.sy, b.sz, s_begin, s_end, ctx->cfg.theta,
-                                                                             ctx->cfg.epsilon2, ctx->cfg.G, b.asx, b.asy, b.asz,
+                                                                             ctx->x, ctx->y, ctx->z, s_begin, s_end, ctx->cfg.theta,
+                                                                             ctx->cfg.epsilon2, ctx->cfg.G, ctx->ax, ctx->ay, ctx->az,
                                                                              b.visits, b.stat_totals);
         } else {
             bh_traverse3_kernel<false><<<g3, NB_G_WARPS * 32, 0, ctx->stream>>>(com, b.meta, b.ctab, b.dev_flags, ctx->n, b.aabb_dev,
-                                                                              b.sx, b.sy, b.sz, s_begin, s_end, ctx->cfg.theta,
-                                                                              ctx->cfg.epsilon2, ctx->cfg.G, b.asx, b.asy, b.asz,
+                                                                              ctx->x, ctx->y, ctx->z, s_begin, s_end, ctx->cfg.theta,
+                                                                              ctx->cfg.epsilon2, ctx->cfg.G, ctx->ax, ctx->ay, ctx->az,
                                                                               b.visits, b.stat_totals);
         }
         NB_LAUNCH_CHECK(ctx);
         return NB_OK;
     }
 #define NB_LAUNCH_WALK(ST, VV)                                                                                          \
-    bh_traverse_kernel<ST, VV><<<grid, threads, 0, ctx->stream>>>(com, b.meta, b.dev_flags, ctx->n, b.aabb_dev, b.sx, b.sy, \
-                                                                  b.sz, s_begin, s_end, ctx->cfg.theta, ctx->cfg.epsilon2,  \
-                                                                  ctx->cfg.G, b.asx, b.asy, b.asz, b.visits, b.stat_totals)
+    bh_traverse_kernel<ST, VV><<<grid, threads, 0, ctx->stream>>>(com, b.meta, b.dev_flags, ctx->n, b.aabb_dev, ctx->x, ctx->y, \
+                                                                  ctx->z, s_begin, s_end, ctx->cfg.theta, ctx->cfg.epsilon2,  \
+                                                                  ctx->cfg.G, ctx->ax, ctx->ay, ctx->az, b.visits, b.stat_totals)
     if (b.stats_enabled) {
         NB_CUDA(ctx, cudaMemsetAsync(b.stat_totals, 0, 8 * sizeof(unsigned long long), ctx->stream));
         NB_CUDA(ctx, cudaMemsetAsync(b.visits, 0, ctx->n * sizeof(uint32_t), ctx->stream));
@@ -479,15 +469,6 @@ int nbk_bh_accel(nb_ctx *ctx, uint64_t s_begin, uint64_t s_end) {
         }
     }
 #undef NB_LAUNCH_WALK
-    NB_LAUNCH_CHECK(ctx);
-    return NB_OK;
-}
-
-// sorted order -> body-id order (ACC_X[i] = ..., BarnesHutAlgorithm.cpp:389-391)
-int nbk_bh_scatter_accel(nb_ctx *ctx) {
-    nb_bh_state &b = ctx->bh;
-    const unsigned grid = (unsigned) ((ctx->n + 255) / 256);
-    scatter_accel_kernel<<<grid, 256, 0, ctx->stream>>>(ctx->n, b.perm, b.asx, b.asy, b.asz, ctx->ax, ctx->ay, ctx->az);
     NB_LAUNCH_CHECK(ctx);
     return NB_OK;
 }

@@ -32,8 +32,7 @@ struct nb_bh_state {
     // per-body, sorted order
     uint64_t *key_hi = nullptr, *key_lo = nullptr;          // octant-path keys (visit-rank digits)
     uint64_t *key_hi_alt = nullptr;                          // radix sort ping-pong
-    uint32_t *perm = nullptr, *perm_alt = nullptr;           // sorted index -> body id
-    double *sx = nullptr, *sy = nullptr, *sz = nullptr, *sm = nullptr;  // positions / masses gathered into sorted order
+    uint32_t *perm = nullptr, *perm_alt = nullptr;           // sorted index -> storage slot before this build's reorder
     int32_t *delta = nullptr;                                // common-prefix digits of sorted neighbours (i, i+1)
     uint32_t *chain_cnt = nullptr, *chain_base = nullptr;    // internal nodes starting at body i, and their scan
     uint32_t *leaf_node = nullptr;                           // node index of the leaf of sorted body i
@@ -48,7 +47,6 @@ struct nb_bh_state {
     void *scan_tmp = nullptr;
     size_t scan_tmp_bytes = 0;
     // results
-    double *asx = nullptr, *asy = nullptr, *asz = nullptr;   // accelerations in sorted order
     uint32_t *visits = nullptr;                              // per-body visit counters (stats)
     unsigned long long *stat_totals = nullptr;               // {visits, accepts}
     // device scalars
@@ -72,10 +70,15 @@ struct nb_ctx {
     std::string last_error;
     std::string device_name;
     uint64_t n = 0, cap = 0;
-    // SoA state (body-id order)
+    // SoA state in STORAGE order.  Storage order is body-id order until the first Barnes-Hut build; every build then
+    // physically permutes the whole state into the new sorted (Morton / DFS) order, so the tree kernels stream it and
+    // consecutive steps permute by a near-identity map.  id[slot] = body id of the slot (valid when !identity_order).
     double *m = nullptr, *x = nullptr, *y = nullptr, *z = nullptr;
     double *vx = nullptr, *vy = nullptr, *vz = nullptr;
     double *ax = nullptr, *ay = nullptr, *az = nullptr;
+    double *alt[10] = {};            // ping-pong partners of m,x,y,z,vx,vy,vz,ax,ay,az (also scratch for read-back)
+    uint32_t *id = nullptr, *id_alt = nullptr;
+    bool identity_order = true;
     double *anorm = nullptr;
     // naive
     nb_src_rec *src = nullptr;
@@ -157,7 +160,8 @@ void nbk_bh_release(nb_ctx *ctx);
 int nbk_bh_aabb(nb_ctx *ctx);
 int nbk_bh_build(nb_ctx *ctx);
 int nbk_bh_accel(nb_ctx *ctx, uint64_t s_begin, uint64_t s_end);
-int nbk_bh_scatter_accel(nb_ctx *ctx);
+int nbk_unpermute(nb_ctx *ctx, int count, const double *const *src, double *const *dst);
+int nbk_permute_in(nb_ctx *ctx, int count, const double *const *src, double *const *dst);
 int nbk_comm_allgather_accel(nb_ctx *ctx, double *ax, double *ay, double *az, uint64_t n);
 void nbk_comm_destroy(nb_ctx *ctx);
 int nbk_comm_allreduce_sum(nb_ctx *ctx, double *buf, size_t count);
