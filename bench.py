@@ -27,6 +27,15 @@ import time
 
 import numpy as np
 
+_REAL_STDOUT = None
+
+
+def emit(line):
+    out = _REAL_STDOUT if _REAL_STDOUT is not None else sys.stdout
+    out.write(json.dumps(line) + "\n")
+    out.flush()
+
+
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
@@ -154,7 +163,7 @@ def run_reference(args, rank, world):
         "e2e": {"value": value, "unit": "interactions/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 def host_threads(O):
@@ -386,7 +395,7 @@ def run_ours(args, rank, local_rank, world):
             "clocks": clocks,
             "bh": bh,
         }
-        print(json.dumps(line), flush=True)
+        emit(line)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
@@ -395,6 +404,12 @@ def run_ours(args, rank, local_rank, world):
 def main():
     args = parse_args()
     rank, local_rank, world = dist_env()
+    # stdout must carry exactly ONE JSON line: libraries (NCCL / c10d print "NCCL version ..." on stdout) are diverted to
+    # stderr for the whole run and the line is written to the saved descriptor at the end
+    global _REAL_STDOUT
+    sys.stdout.flush()
+    _REAL_STDOUT = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
     if args.impl == "reference":
         run_reference(args, rank, world)
         return

@@ -132,6 +132,8 @@ def default_config(**overrides):
             cfg.reserved[0] = int(v)
         elif k in ("single_phase_walk", "bh_variant"):
             cfg.reserved[1] = int(v)
+        elif k == "naive_segments":
+            cfg.reserved[4] = int(v)
         elif k == "walk_variant":
             cfg.reserved[3] = int(v)
         elif k == "naive_variant":

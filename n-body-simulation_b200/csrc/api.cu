@@ -104,7 +104,7 @@ void nb_destroy(nb_ctx *ctx) {
     nb_free(&ctx->m); nb_free(&ctx->x); nb_free(&ctx->y); nb_free(&ctx->z);
     nb_free(&ctx->vx); nb_free(&ctx->vy); nb_free(&ctx->vz);
     nb_free(&ctx->ax); nb_free(&ctx->ay); nb_free(&ctx->az);
-    nb_free(&ctx->anorm); nb_free(&ctx->src); nb_free(&ctx->e_partial);
+    nb_free(&ctx->anorm); nb_free(&ctx->src); nb_free(&ctx->e_partial); nb_free(&ctx->naive_partial);
     for (int k = 0; k < 10; ++k) nb_free(&ctx->alt[k]);
     nb_free(&ctx->id); nb_free(&ctx->id_alt);
     if (ctx->h_pinned) cudaFreeHost(ctx->h_pinned);

@@ -83,6 +83,8 @@ struct nb_ctx {
     // naive
     nb_src_rec *src = nullptr;
     uint64_t src_cap = 0;
+    double *naive_partial = nullptr;  // per-segment partial accelerations when the source range is split
+    size_t naive_partial_cap = 0;
     // energy
     double *e_partial = nullptr;  // 2*n doubles: kinetic, potential per body
     // host staging (pinned)

@@ -73,10 +73,10 @@ __global__ void pack_sources_kernel(const double *__restrict__ m, const double *
 
 template <int IPT, bool PRECISE, int UNROLL, int MINB>
 __global__ void __launch_bounds__(NB_NAIVE_THREADS, MINB)
-naive_accel_kernel(const nb_src_rec *__restrict__ src, uint32_t n_tiles, uint32_t tile_len,
+naive_accel_kernel(const nb_src_rec *__restrict__ src, uint32_t n_tiles_total, uint32_t seg_tiles, uint32_t tile_len,
                    const double *__restrict__ x, const double *__restrict__ y, const double *__restrict__ z,
                    uint64_t i_begin, uint64_t i_end, double eps2, double G, double *__restrict__ ax,
-                   double *__restrict__ ay, double *__restrict__ az) {
+                   double *__restrict__ ay, double *__restrict__ az, double *__restrict__ partial) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     uint64_t *full = reinterpret_cast<uint64_t *>(smem_raw);
     uint64_t *empty = full + NB_NAIVE_STAGES;
@@ -85,6 +85,11 @@ naive_accel_kernel(const nb_src_rec *__restrict__ src, uint32_t n_tiles, uint32_
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
     const uint32_t tile_bytes = tile_len * (uint32_t) sizeof(nb_src_rec);
+    // blockIdx.y = source segment: this CTA sums the tiles [t0, t0 + n_tiles) only (finer work quanta for small target
+    // counts; the segments are added in ascending order by naive_reduce_kernel)
+    const uint32_t t0 = blockIdx.y * seg_tiles;
+    const uint32_t n_tiles = n_tiles_total - t0 < seg_tiles ? n_tiles_total - t0 : seg_tiles;
+    src += (size_t) t0 * tile_len;
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < NB_NAIVE_STAGES; ++s) {
@@ -159,15 +164,41 @@ naive_accel_kernel(const nb_src_rec *__restrict__ src, uint32_t n_tiles, uint32_
         if (lane == 0) mbar_arrive(&empty[s]);
     }
 
+    const uint64_t count = i_end - i_begin;
 #pragma unroll
     for (int k = 0; k < IPT; ++k) {
         const uint64_t i = base + (uint64_t) k * TPB;
         if (i < i_end) {
-            ax[i] = accx[k] * G;
-            ay[i] = accy[k] * G;
-            az[i] = accz[k] * G;
+            if (gridDim.y == 1) {
+                ax[i] = accx[k] * G;
+                ay[i] = accy[k] * G;
+                az[i] = accz[k] * G;
+            } else {
+                double *p = partial + (size_t) blockIdx.y * 3 * count + (i - i_begin);
+                p[0] = accx[k];
+                p[count] = accy[k];
+                p[2 * count] = accz[k];
+            }
         }
     }
+}
+
+// deterministic sum of the source segments (ascending), then the final scale by G (NaiveAlgorithm.cpp:349-351)
+__global__ void __launch_bounds__(256)
+naive_reduce_kernel(const double *__restrict__ partial, uint32_t segments, uint64_t i_begin, uint64_t count, double G,
+                    double *__restrict__ ax, double *__restrict__ ay, double *__restrict__ az) {
+    const uint64_t i = (uint64_t) blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= count) return;
+    double sx = 0, sy = 0, sz = 0;
+    for (uint32_t s = 0; s < segments; ++s) {
+        const double *p = partial + (size_t) s * 3 * count + i;
+        sx += p[0];
+        sy += p[count];
+        sz += p[2 * count];
+    }
+    ax[i_begin + i] = sx * G;
+    ay[i_begin + i] = sy * G;
+    az[i_begin + i] = sz * G;
 }
 
 // DFMA-chain microbenchmark: CHAINS independent dependent-FMA chains per thread, 2 flops per DFMA.
@@ -192,14 +223,37 @@ __global__ void __launch_bounds__(1024) fp64_peak_kernel(double *out, int iters,
 template <int IPT, bool PRECISE, int UNROLL = 4, int MINB = 2>
 int launch_naive(nb_ctx *ctx, uint32_t n_tiles, uint32_t tile_len, uint64_t i_begin, uint64_t i_end) {
     const uint64_t per_cta = (uint64_t) NB_NAIVE_CONSUMER_WARPS * 32 * IPT;
-    const uint64_t grid = (i_end - i_begin + per_cta - 1) / per_cta;
+    const uint64_t count = i_end - i_begin;
+    const uint64_t grid = (count + per_cta - 1) / per_cta;
     const size_t smem = 128 + (size_t) NB_NAIVE_STAGES * tile_len * sizeof(nb_src_rec);
+    // work quanta: aim for >= 32 CTAs per SM so the tail of the last wave is a few percent; split the source range
+    // into segments when there are too few target tiles (small N, or a rank's slice on many GPUs)
+    uint32_t segments = 1;
+    const uint64_t want = (uint64_t) ctx->sm_count * 32;
+    if (ctx->cfg.reserved[4] > 0) segments = (uint32_t) ctx->cfg.reserved[4];
+    else if (grid < want) segments = (uint32_t) ((want + grid - 1) / grid);
+    if (segments > 32) segments = 32;
+    if (segments > n_tiles) segments = n_tiles;
+    uint32_t seg_tiles = (n_tiles + segments - 1) / segments;
+    segments = (n_tiles + seg_tiles - 1) / seg_tiles;
+    if (segments > 1) {
+        const size_t need = (size_t) segments * 3 * count;
+        if (need > ctx->naive_partial_cap) {
+            NB_CHECK(nb_alloc(ctx, &ctx->naive_partial, need));
+            ctx->naive_partial_cap = need;
+        }
+    }
     auto kern = naive_accel_kernel<IPT, PRECISE, UNROLL, MINB>;
     NB_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
-    kern<<<(unsigned) grid, NB_NAIVE_THREADS, smem, ctx->stream>>>(ctx->src, n_tiles, tile_len, ctx->x, ctx->y, ctx->z,
-                                                                   i_begin, i_end, ctx->cfg.epsilon2, ctx->cfg.G,
-                                                                   ctx->ax, ctx->ay, ctx->az);
+    kern<<<dim3((unsigned) grid, segments), NB_NAIVE_THREADS, smem, ctx->stream>>>(
+        ctx->src, n_tiles, seg_tiles, tile_len, ctx->x, ctx->y, ctx->z, i_begin, i_end, ctx->cfg.epsilon2, ctx->cfg.G, ctx->ax,
+        ctx->ay, ctx->az, ctx->naive_partial);
     NB_LAUNCH_CHECK(ctx);
+    if (segments > 1) {
+        naive_reduce_kernel<<<(unsigned) ((count + 255) / 256), 256, 0, ctx->stream>>>(ctx->naive_partial, segments, i_begin,
+                                                                                    count, ctx->cfg.G, ctx->ax, ctx->ay, ctx->az);
+        NB_LAUNCH_CHECK(ctx);
+    }
     return NB_OK;
 }
 

@@ -1,5 +1,6 @@
-"""Two-rank run on real GPUs (skipped unless >= 2 GPUs are visible): naive and Barnes-Hut accelerations computed by
-target-sharded ranks + NCCL all-gather must equal the single-GPU result bit for bit (same kernels, same order)."""
+"""Two-rank run on real GPUs (skipped unless >= 2 GPUs are visible): accelerations computed by target-sharded ranks +
+NCCL all-gather must equal the single-GPU result (Barnes-Hut: bit for bit; naive: to 1e-13, its source-range
+segmentation depends on the slice size)."""
 import os
 import subprocess
 import sys
@@ -33,7 +34,8 @@ ctx.set_bodies(m, x, y, z, vx, vy, vz)
 for c in (ref, ctx):
     c.naive_accel()
 a, b = ref.accelerations(), ctx.accelerations()
-assert all(np.array_equal(u, v) for u, v in zip(a, b)), "naive sharded != single"
+# the source range may be split into a different number of segments for a slice: rounding-level differences only
+assert all(np.allclose(u, v, rtol=1e-13, atol=0) for u, v in zip(a, b)), "naive sharded != single"
 for c in (ref, ctx):
     c.bh_build(); c.bh_accel(); c.leapfrog_part1(0.01); c.bh_build(); c.bh_accel(); c.leapfrog_part2(0.01)
 a, b = ref.accelerations() + ref.positions() + ref.velocities(), ctx.accelerations() + ctx.positions() + ctx.velocities()

@@ -62,6 +62,17 @@ def test_naive_block_size_and_register_blocking(nb, oracle, block_size, ipt):
     c.close()
 
 
+@pytest.mark.parametrize("segments", [1, 2, 5, 32])
+def test_naive_source_segments(nb, oracle, segments):
+    """Splitting the source range across CTAs (work quanta for small target counts) only reorders the partial sums."""
+    m, x, y, z, *_ = nb.generators.plummer(7000, seed=17)
+    c = nb.Context(device=0, naive_segments=segments, block_size=64)
+    c.set_bodies(m, x, y, z)
+    c.naive_accel()
+    assert relerr(c.accelerations(), oracle.naive_accel(m, x, y, z)) <= TOL
+    c.close()
+
+
 @pytest.mark.parametrize("opt_stage", [0, 1, 2])
 def test_naive_opt_stages_agree(nb, oracle, opt_stage):
     m, x, y, z, *_ = nb.generators.uniform_sphere(777, seed=8)

@@ -153,6 +153,18 @@ def t_naive_sweep():
             c.close()
 
 
+def t_naive_segments():
+    section("naive segments")
+    for n in (1 << 20, 1 << 17):
+        m, x, y, z, vx, vy, vz = nb.generators.plummer(n, seed=1)
+        for seg in (0, 1, 2, 4, 8, 16):
+            c = nb.Context(naive_segments=seg, block_size=256)
+            c.set_bodies(m, x, y, z, vx, vy, vz); c.enable_timers(True)
+            c.naive_accel(); c.naive_accel(); ms = c.timers()["Acceleration Kernel Time"]
+            print("n=%d segments=%d: %.2f ms  %.4e inter/s  %.2f TF(21)" % (n, seg, ms, n * n / ms * 1e3, 21.0 * n * n / ms * 1e3 / 1e12), flush=True)
+            c.close()
+
+
 def t_perf_bh():
     section("perf bh")
     for gen, n, theta in (("plummer", 1 << 20, 0.5), ("uniform_sphere", 1 << 22, 0.5), ("uniform_sphere", 1 << 24, 0.5)):
