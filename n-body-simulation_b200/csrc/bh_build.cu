@@ -31,6 +31,7 @@
 #define NB_NONE 0xffffffffu
 #define NB_FLAG_DEPTH 1u
 #define NB_FLAG_POOL 2u
+#define NB_LEVELS 64
 
 namespace {
 
@@ -288,6 +289,62 @@ emit_kernel(const uint64_t *__restrict__ hi, const uint64_t *__restrict__ lo, co
     leaf_node[i] = (uint32_t) leaf;
 }
 
+// ---- 4b. per-depth lists of internal nodes (dense work lists for the centre-of-mass levels) ---------------------------------
+// level[0..63] = node count per depth, level[64..127] = start of the depth's segment in `list`, level[128..191] = fill cursor
+__global__ void __launch_bounds__(256)
+level_count_kernel(const int32_t *__restrict__ delta, uint64_t n, uint32_t *__restrict__ level) {
+    __shared__ uint32_t cnt[NB_LEVELS];
+    if (threadIdx.x < NB_LEVELS) cnt[threadIdx.x] = 0;
+    __syncthreads();
+    const uint64_t i = (uint64_t) blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) {
+        const int d_prev = i > 0 ? delta[i - 1] : -1;
+        const int d_cur = delta[i];
+        for (int d = d_prev + 1; d <= d_cur; ++d) atomicAdd(&cnt[d], 1u);
+    }
+    __syncthreads();
+    if (threadIdx.x < NB_LEVELS && cnt[threadIdx.x]) atomicAdd(&level[threadIdx.x], cnt[threadIdx.x]);
+}
+
+__global__ void level_scan_kernel(uint32_t *__restrict__ level) {
+    if (threadIdx.x == 0) {
+        uint32_t run = 0;
+        for (int d = 0; d < NB_LEVELS; ++d) {
+            level[NB_LEVELS + d] = run;
+            level[2 * NB_LEVELS + d] = 0;
+            run += level[d];
+        }
+    }
+}
+
+__global__ void __launch_bounds__(256)
+level_fill_kernel(const int32_t *__restrict__ delta, const uint32_t *__restrict__ base, uint64_t n,
+                  const uint32_t *__restrict__ flags, uint32_t *__restrict__ level, uint32_t *__restrict__ list) {
+    __shared__ uint32_t cnt[NB_LEVELS], start[NB_LEVELS];
+    if (flags[0] & NB_FLAG_POOL) return;
+    if (threadIdx.x < NB_LEVELS) cnt[threadIdx.x] = 0;
+    __syncthreads();
+    const uint64_t i = (uint64_t) blockIdx.x * blockDim.x + threadIdx.x;
+    int d_prev = 0, d_cur = -1;
+    if (i < n) {
+        d_prev = i > 0 ? delta[i - 1] : -1;
+        d_cur = delta[i];
+        for (int d = d_prev + 1; d <= d_cur; ++d) atomicAdd(&cnt[d], 1u);
+    }
+    __syncthreads();
+    if (threadIdx.x < NB_LEVELS) {
+        const uint32_t c = cnt[threadIdx.x];
+        start[threadIdx.x] = level[NB_LEVELS + threadIdx.x] + (c ? atomicAdd(&level[2 * NB_LEVELS + threadIdx.x], c) : 0u);
+        cnt[threadIdx.x] = 0;
+    }
+    __syncthreads();
+    if (i < n) {
+        const uint32_t head = (uint32_t) (i + base[i]);
+        for (int d = d_prev + 1; d <= d_cur; ++d)
+            list[start[d] + atomicAdd(&cnt[d], 1u)] = head + (uint32_t) (d - d_prev - 1);
+    }
+}
+
 // ---- 5. centre of mass ------------------------------------------------------------------------------------------------------
 // leaf: prepareCenterOfMass (BarnesHutOctree.cpp:216-226); internal: the octant-ordered sum of :299-317.
 // Level-synchronous, deepest level first: one launch per depth, one thread per body; the thread owns the internal node
@@ -317,17 +374,15 @@ com_leaf_kernel(uint64_t n, const uint32_t *__restrict__ flags_in, const double 
 }
 
 __global__ void __launch_bounds__(256)
-com_level_kernel(int depth, uint64_t n, const uint32_t *__restrict__ flags_in, const int32_t *__restrict__ delta,
-                 const uint32_t *__restrict__ base, const uint2 *__restrict__ meta, double *com, double *msum4,
+com_level_kernel(int depth, const uint32_t *__restrict__ flags_in, const uint32_t *__restrict__ level,
+                 const uint32_t *__restrict__ list, const uint2 *__restrict__ meta, double *com, double *msum4,
                  uint32_t *__restrict__ ctab /* optional child table for the group traversal */) {
     // flags[2] = deepest leaf = 1 + deepest internal node: nothing to do for the levels below the tree
     if ((uint32_t) depth >= flags_in[2] || (flags_in[0] & NB_FLAG_POOL)) return;
-    for (uint64_t i = (uint64_t) blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (uint64_t) gridDim.x * blockDim.x) {
-        const int d_cur = delta[i];
-        if (depth > d_cur) continue;
-        const int d_prev = i > 0 ? delta[i - 1] : -1;
-        if (depth <= d_prev) continue;
-        const uint32_t p = (uint32_t) (i + base[i] + (uint64_t) (depth - d_prev - 1));
+    const uint32_t count = level[depth];
+    const uint32_t *nodes = list + level[NB_LEVELS + depth];
+    for (uint32_t k = blockIdx.x * blockDim.x + threadIdx.x; k < count; k += gridDim.x * blockDim.x) {
+        const uint32_t p = nodes[k];
         const uint32_t end = meta[p].x;
         // children (leaves, or depth+1 nodes finished by the previous launch), indexed by their visit rank
         uint32_t child[8];
@@ -392,6 +447,8 @@ int nbk_bh_reserve(nb_ctx *ctx) {
     NB_CHECK(nb_alloc(ctx, &b.com, 4 * cap_nodes));
     NB_CHECK(nb_alloc(ctx, &b.msum, 4 * cap_nodes));
     NB_CHECK(nb_alloc(ctx, &b.meta, cap_nodes));
+    NB_CHECK(nb_alloc(ctx, &b.level, 3 * NB_LEVELS));
+    NB_CHECK(nb_alloc(ctx, &b.level_list, cap_nodes - n + 8));
     NB_CHECK(nb_alloc(ctx, &b.body_count, cap_nodes));
     const size_t scratch = nbprim::rs_scratch_elems(nb) + nbprim::scan_tiles_for(nb) + 64;
     NB_CHECK(nb_alloc(ctx, &b.hist, scratch));
@@ -411,7 +468,7 @@ void nbk_bh_release(nb_ctx *ctx) {
     nb_free(&b.key_hi); nb_free(&b.key_lo); nb_free(&b.key_hi_alt); nb_free(&b.perm); nb_free(&b.perm_alt);
     nb_free(&b.delta); nb_free(&b.chain_cnt);
     nb_free(&b.chain_base); nb_free(&b.leaf_node); 
-    nb_free(&b.visits); nb_free(&b.com); nb_free(&b.msum); nb_free(&b.meta); nb_free(&b.ctab); 
+    nb_free(&b.visits); nb_free(&b.com); nb_free(&b.msum); nb_free(&b.meta); nb_free(&b.level); nb_free(&b.level_list); nb_free(&b.ctab); 
     nb_free(&b.body_count); nb_free(&b.hist); nb_free(&b.aabb_dev);
     nb_free(&b.aabb_partial); nb_free(&b.dev_flags); nb_free(&b.stat_totals);
     b.cap_bodies = b.cap_nodes = 0;
@@ -483,6 +540,14 @@ int nbk_bh_build(nb_ctx *ctx) {
         emit_kernel<<<g128, 128, 0, ctx->stream>>>(hi, lo, b.delta, b.chain_base, n, b.cap_nodes, b.dev_flags, b.meta,
                                                    b.body_count, b.leaf_node);
         NB_LAUNCH_CHECK(ctx);
+        // dense per-depth node lists for the centre-of-mass levels
+        NB_CUDA(ctx, cudaMemsetAsync(b.level, 0, 3 * NB_LEVELS * sizeof(uint32_t), ctx->stream));
+        level_count_kernel<<<g256, 256, 0, ctx->stream>>>(b.delta, n, b.level);
+        NB_LAUNCH_CHECK(ctx);
+        level_scan_kernel<<<1, 32, 0, ctx->stream>>>(b.level);
+        NB_LAUNCH_CHECK(ctx);
+        level_fill_kernel<<<g256, 256, 0, ctx->stream>>>(b.delta, b.chain_base, n, b.dev_flags, b.level, b.level_list);
+        NB_LAUNCH_CHECK(ctx);
     }
     {
         nb_timer_scope t(ctx, NB_T_COM);
@@ -493,8 +558,8 @@ int nbk_bh_build(nb_ctx *ctx) {
         if (want_ctab && !b.ctab) NB_CHECK(nb_alloc(ctx, &b.ctab, 8 * b.cap_nodes));
         b.ctab_valid = want_ctab;
         for (int depth = NB_MAX_TREE_DEPTH - 1; depth >= 0; --depth) {
-            com_level_kernel<<<level_grid, 256, 0, ctx->stream>>>(depth, n, b.dev_flags, b.delta, b.chain_base, b.meta,
-                                                                  b.com, b.msum, want_ctab ? b.ctab : nullptr);
+            com_level_kernel<<<level_grid, 256, 0, ctx->stream>>>(depth, b.dev_flags, b.level, b.level_list, b.meta, b.com,
+                                                                  b.msum, want_ctab ? b.ctab : nullptr);
             NB_LAUNCH_CHECK(ctx);
         }
     }

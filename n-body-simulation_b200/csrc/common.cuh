@@ -40,6 +40,7 @@ struct nb_bh_state {
     double *com = nullptr;                                   // 4 doubles per node
     double *msum = nullptr;                                  // 4 doubles per node: {sum m*x, sum m*y, sum m*z, sum m} (reference's massCenters_* / sumOfMasses)
     uint2 *meta = nullptr;
+    uint32_t *level = nullptr, *level_list = nullptr;        // per-depth internal-node lists (count / start / cursor, nodes)
     uint32_t *ctab = nullptr;                                // 8 child node indices per node, by visit rank (NB_NONE = empty octant)
     uint32_t *body_count = nullptr;
     // sort scratch
