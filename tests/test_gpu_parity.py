@@ -223,6 +223,46 @@ def test_tree_node_set_and_com_match_oracle(nb, oracle, ctx, n, gen, seed):
     assert np.array_equal(ctx.bh_sorted_bodies(), t.sorted_bodies)
 
 
+def test_tree_with_bodies_on_cell_boundaries(nb, oracle, ctx):
+    """Lattice positions (multiples of 2^-4 in a cube that the AABB reproduces exactly) put many bodies exactly on cell
+    mid-planes: the strict compares `y > mid`, `x > mid`, `z < mid` (ParallelOctreeTopDownSubtrees.cpp:400-406) decide."""
+    g = np.arange(17) / 16.0
+    X, Y, Z = np.meshgrid(g, g, g, indexing="ij")
+    x, y, z = X.ravel().copy(), Y.ravel().copy(), Z.ravel().copy()
+    rng = np.random.default_rng(5)
+    keep = rng.random(x.size) < 0.6
+    keep[0] = keep[-1] = True                      # keep the corners so the cube is [0, 1]^3
+    x, y, z = x[keep], y[keep], z[keep]
+    m = 1.0e24 * (1.0 + rng.random(x.size))
+    ctx.set_theta(0.5)
+    ctx.set_bodies(m, x, y, z)
+    ctx.bh_enable_stats(True)
+    ctx.bh_build(); ctx.bh_accel()
+    t = oracle.Tree(m, x, y, z)
+    assert np.array_equal(ctx.bh_aabb(), t.aabb()) and t.aabb()[6] == 1.0
+    assert_same_tree(ctx.bh_export_canonical(), t.canonical())
+    assert np.array_equal(ctx.bh_sorted_bodies(), t.sorted_bodies)
+    ax, ay, az, st = t.accel(0.5, stats=True)
+    assert np.array_equal(ctx.bh_stats(per_body=True)[2], st[:, 1].astype(np.uint32))
+    assert relerr(ctx.accelerations(), (ax, ay, az)) <= TOL
+
+
+def test_tree_two_clusters_negative_coordinates(nb, oracle, ctx):
+    """Two well separated clumps (deep, unbalanced tree; long single-child chains) in the negative octants."""
+    m1, x1, y1, z1, *_ = nb.generators.plummer(3000, seed=31, a=0.01, r_max=20.0)
+    m2, x2, y2, z2, *_ = nb.generators.uniform_sphere(2000, seed=32, radius=0.05)
+    x = np.concatenate([x1 - 40.0, x2 - 3.0]); y = np.concatenate([y1 - 25.0, y2 - 30.0]); z = np.concatenate([z1 - 7.0, z2 - 9.0])
+    m = np.concatenate([m1, m2])
+    c = nb.Context(device=0, theta=0.7, storage_size_param=64)
+    c.set_bodies(m, x, y, z)
+    c.bh_build(); c.bh_accel()
+    t = oracle.Tree(m, x, y, z, storage_param=64)
+    assert c.bh_tree_info().max_depth == t.max_depth
+    assert_same_tree(c.bh_export_canonical(), t.canonical())
+    assert relerr(c.accelerations(), t.accel(0.7)) <= TOL
+    c.close()
+
+
 def test_tree_with_cloud_far_from_origin(nb, oracle, ctx):
     """The AABB always contains the origin."""
     m, x, y, z, *_ = nb.generators.uniform_sphere(500, seed=9)

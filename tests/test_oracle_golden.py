@@ -65,6 +65,18 @@ def test_sort_bodies_for_subtrees(oracle):
     assert list(sorted_bodies[:9]) == [0, 1, 2, 3, 5, 6, 7, 8, 9]
 
 
+def test_octant_code_strict_compares(oracle):
+    """o = 4*(y > mid) + 2*(x > mid) + 1*(z < mid) with strict compares (BarnesHutOctree.cpp:586-591): a body exactly on
+    every mid-plane of the root cube [0,2]^3 falls in octant 0 (not upper, not right, not back)."""
+    x = [0.0, 2.0, 1.0]; y = [0.0, 2.0, 1.0]; z = [0.0, 2.0, 1.0]
+    t = oracle.Tree([1.0, 1.0, 1.0], x, y, z)
+    c = t.canonical()
+    kids = [(int(k), int(b)) for d, k, b in zip(c["depth"], c["kind"], c["body"]) if d == 1]
+    # octant order 0..7: body 2 (centre) shares octant 0 with nobody: body 0 at the origin has z < mid -> octant 1;
+    # body 1 at (2,2,2): upper, right, not back -> octant 6
+    assert kids[0] == (1, 2) and kids[1] == (1, 0) and kids[6] == (1, 1)
+
+
 def test_two_body_force_known_answer(oracle):
     # a = G m / (r^2 + eps2)^(3/2) * r along the separation (NaiveAlgorithm.cpp:332-351)
     G, eps2 = oracle.gravitational_constant(), oracle.epsilon2()

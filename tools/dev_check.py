@@ -165,6 +165,17 @@ def t_naive_segments():
             c.close()
 
 
+def t_energy_perf():
+    section("energy perf")
+    for n in (1 << 17, 1 << 19, 1 << 20):
+        m, x, y, z, vx, vy, vz = nb.generators.plummer(n, seed=1)
+        c = nb.Context(); c.set_bodies(m, x, y, z, vx, vy, vz); c.enable_timers(True)
+        c.energy(); e = c.energy(); ms = c.timers()["Energy"]
+        pairs = n * (n - 1) / 2
+        print("n=%d: %.2f ms  %.3e pairs/s  (12 DP ops/pair -> %.2f T DP-inst-lanes/s)" % (n, ms, pairs / ms * 1e3, 12 * pairs / ms * 1e3 / 1e12), e, flush=True)
+        c.close()
+
+
 def t_perf_bh():
     section("perf bh")
     for gen, n, theta in (("plummer", 1 << 20, 0.5), ("uniform_sphere", 1 << 22, 0.5), ("uniform_sphere", 1 << 24, 0.5)):
