@@ -44,8 +44,8 @@ BH_BYTES_PER_VISIT = 40.0            # com xyz + mass (32 B) + skip/m
 BH_BYTES_PER_BODY = 48.0             # position in, acceleration out
 NAIVE_TILE = 256                     # --block_size used for the benchmark (shared-memory tile length)
 # dram__bytes_read.sum + dram__bytes_write.sum per launch from the `ncu --set full` captures summarised under profiles/
-# (naive: N = 2^20, profiles/naive_accel_r01.txt; Barnes-Hut walk: N = 2^22, profiles/bh_traverse_r01_singlephase.txt)
-NCU_TRAFFIC_BYTES = {("naive", 1 << 20): 90.7392e6 + 25.0391e6, ("bh", 1 << 22): 400.0858e6 + 90.6862e6}
+# (naive: N = 2^20, profiles/naive_accel_r01.txt; Barnes-Hut walk: N = 2^22, profiles/bh_traverse_r01.txt)
+NCU_TRAFFIC_BYTES = {("naive", 1 << 20): 121.3425e6 + 55.0454e6, ("bh", 1 << 22): 400.5560e6 + 93.6484e6}
 
 
 def parse_args():

@@ -357,7 +357,9 @@ __device__ __forceinline__ void store_node(double *com, double *msum4, uint32_t 
     double2 *s2 = reinterpret_cast<double2 *>(msum4 + 4 * (size_t) node);
     s2[0] = make_double2(sx, sy);
     s2[1] = make_double2(sz, m);
-    const double cx = __ddiv_rn(sx, m), cy = __ddiv_rn(sy, m), cz = __ddiv_rn(sz, m);
+    // massless cells are skipped by the traversal; keep their record finite
+    const bool has_mass = m != 0.0;
+    const double cx = has_mass ? __ddiv_rn(sx, m) : 0.0, cy = has_mass ? __ddiv_rn(sy, m) : 0.0, cz = has_mass ? __ddiv_rn(sz, m) : 0.0;
     double2 *c2 = reinterpret_cast<double2 *>(com + 4 * (size_t) node);
     c2[0] = make_double2(cx, cy);
     c2[1] = make_double2(cz, m);

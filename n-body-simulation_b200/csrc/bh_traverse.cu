@@ -33,7 +33,7 @@ __device__ __forceinline__ double scale_pow2(double v, uint32_t depth) {  // v *
 }
 
 template <bool STATS, int V>
-__global__ void __launch_bounds__(256, (V & 4) ? 5 : 1)
+__global__ void __launch_bounds__(256, (V & 8) ? 6 : ((V & 4) ? 5 : 1))
 bh_traverse_kernel(const double4 *__restrict__ com, const uint2 *__restrict__ meta, const uint32_t *__restrict__ flags,
                    uint64_t n_bodies, const double *__restrict__ aabb, const double *__restrict__ sx,
                    const double *__restrict__ sy, const double *__restrict__ sz, uint64_t s_begin, uint64_t s_end,
@@ -88,11 +88,17 @@ bh_traverse_kernel(const double4 *__restrict__ com, const uint2 *__restrict__ me
         if (next == cur) {
             const double dx = c.x - px, dy = c.y - py, dz = c.z - pz;
             const double d2 = fma(dz, dz, fma(dy, dy, dx * dx));
+            // SUM_MASSES == 0 nodes are invisible in the reference (BarnesHutAlgorithm.cpp:349): massless bodies, and
+            // cells that hold only massless bodies, are neither counted nor opened
+            const bool massless = (__double2hiint(c.w) | __double2loint(c.w)) == 0;
             bool interact;
             if (mt.y & NB_LEAF_FLAG) {
-                interact = (mt.y & NB_PAYLOAD_MASK) != me;  // own leaf skipped (BarnesHutAlgorithm.cpp:349)
+                interact = (mt.y & NB_PAYLOAD_MASK) != me && !massless;  // own leaf skipped (:349)
                 next = cur + 1;
                 if (STATS) nvis += interact ? 1u : 0u;
+            } else if (massless) {
+                interact = false;
+                next = max(mt.x, cur + 1);
             } else {
                 const uint32_t depth = mt.y & NB_PAYLOAD_MASK;
                 bool accept = d2 > (TABLE_FREE ? scale_pow4(hi0, depth) : t_hi[depth]);
@@ -279,7 +285,10 @@ bh_traverse3_kernel(const double4 *__restrict__ com, const uint2 *__restrict__ m
             const double4 c = com[item.x];
             kid_lo = reinterpret_cast<const uint4 *>(ctab)[2 * (size_t) item.x];
             kid_hi = reinterpret_cast<const uint4 *>(ctab)[2 * (size_t) item.x + 1];
-            if (mt.y & NB_LEAF_FLAG) {
+            const bool massless = (__double2hiint(c.w) | __double2loint(c.w)) == 0;  // invisible in the reference (:349)
+            if (massless) {
+                cls = 0;
+            } else if (mt.y & NB_LEAF_FLAG) {
                 const uint64_t sidx = mt.y & NB_PAYLOAD_MASK;  // the leaf's own body never interacts with itself
                 imask = item.y;
                 if (sidx >= wbase && sidx < wbase + 32) imask &= ~(1u << (uint32_t) (sidx - wbase));
@@ -465,6 +474,7 @@ int nbk_bh_accel(nb_ctx *ctx, uint64_t s_begin, uint64_t s_end) {
             case 5: NB_LAUNCH_WALK(false, 5); break;
             case 7: NB_LAUNCH_WALK(false, 7); break;
             case 8: NB_LAUNCH_WALK(false, 0); break;
+            case 9: NB_LAUNCH_WALK(false, 9); break;
             default: NB_LAUNCH_WALK(false, 5); break;  // table-free thresholds, 48 registers (best of the sweep)
         }
     }

@@ -339,6 +339,27 @@ def test_bh_accelerations_and_visit_counts(nb, oracle, n, gen, seed, theta):
     c.close()
 
 
+@pytest.mark.parametrize("variant", [0, 3])
+def test_bh_massless_bodies_are_invisible(nb, oracle, variant):
+    """The reference skips nodes with SUM_MASSES == 0 (BarnesHutAlgorithm.cpp:349): massless bodies exert no force and
+    are not counted as visits, but they are still accelerated (tracer particles)."""
+    m, x, y, z, *_ = nb.generators.plummer(3000, seed=41)
+    m[::7] = 0.0
+    m[100:140] = 0.0   # a few cells that hold only massless bodies
+    c = nb.Context(device=0, theta=0.5, bh_variant=variant)
+    c.set_bodies(m, x, y, z)
+    c.bh_enable_stats(True)
+    c.bh_build(); c.bh_accel()
+    got = c.accelerations()
+    ax, ay, az, st = oracle.Tree(m, x, y, z).accel(0.5, stats=True)
+    assert np.array_equal(c.bh_stats(per_body=True)[2], st[:, 1].astype(np.uint32))
+    assert all(np.isfinite(g).all() for g in got)
+    assert relerr(got, (ax, ay, az)) <= TOL
+    c.naive_accel()
+    assert relerr(c.accelerations(), oracle.naive_accel(m, x, y, z)) <= TOL
+    c.close()
+
+
 @pytest.mark.parametrize("wg", [32, 64, 128, 256])
 def test_bh_work_group_size_is_geometry_only(nb, oracle, wg):
     m, x, y, z, *_ = nb.generators.plummer(3000, seed=5)

@@ -182,3 +182,27 @@ def test_uniform_sphere_shape(nb):
     r = np.sqrt(x * x + y * y + z * z)
     assert r.max() <= 1.0 and np.median(r) == pytest.approx(0.5 ** (1 / 3), rel=0.03)
     assert not vx.any()
+
+
+def test_header_is_plain_c(tmp_path):
+    """The drop-in boundary is a C ABI: the header must compile as C99 (no C++-isms, no torch types) and a C program must
+    link against the library using only what the header declares."""
+    header = os.path.join(ROOT, "include", "nbody_b200.h")
+    subprocess.check_call(["gcc", "-std=c99", "-Wall", "-Wextra", "-pedantic", "-Werror", "-fsyntax-only", "-x", "c", header])
+    src = tmp_path / "probe.c"
+    src.write_text('#include "nbody_b200.h"\n#include <stdio.h>\n'
+                   'int main(void) { nb_config c; nb_ctx *ctx = 0; nb_config_default(&c);\n'
+                   '  int rc = nb_create(&c, &ctx);\n'
+                   '  printf("%d %d %s %.17g\\n", nb_abi_version(), rc, nb_status_string(rc), c.G);\n'
+                   '  if (ctx) nb_destroy(ctx); return 0; }\n')
+    exe = tmp_path / "probe"
+    lib_dir = os.path.join(ROOT, "n-body-simulation_b200")
+    subprocess.check_call(["gcc", "-std=c99", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe), "-L", lib_dir,
+                           "-lnbody_b200", "-Wl,-rpath," + lib_dir])
+    out = subprocess.run([str(exe)], capture_output=True, text=True)
+    assert out.returncode == 0
+    fields = out.stdout.split()
+    assert fields[0] == "1"
+    import torch
+    if not torch.cuda.is_available():
+        assert fields[1] == "-2"          # NB_ERR_NO_DEVICE: no CPU fallback
