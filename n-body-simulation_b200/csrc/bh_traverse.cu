@@ -89,8 +89,10 @@ bh_traverse_kernel(const double4 *__restrict__ com, const uint2 *__restrict__ me
             const double dx = c.x - px, dy = c.y - py, dz = c.z - pz;
             const double d2 = fma(dz, dz, fma(dy, dy, dx * dx));
             // SUM_MASSES == 0 nodes are invisible in the reference (BarnesHutAlgorithm.cpp:349): massless bodies, and
-            // cells that hold only massless bodies, are neither counted nor opened
-            const bool massless = (__double2hiint(c.w) | __double2loint(c.w)) == 0;
+            // cells that hold only massless bodies, are neither counted nor opened.  Their contribution is exactly
+            // 0.0 either way (the build stores a finite record for them), so only the instrumented build pays for the
+            // check that keeps the visit counts identical to the reference's.
+            const bool massless = STATS && (__double2hiint(c.w) | __double2loint(c.w)) == 0;
             bool interact;
             if (mt.y & NB_LEAF_FLAG) {
                 interact = (mt.y & NB_PAYLOAD_MASK) != me && !massless;  // own leaf skipped (:349)
@@ -285,7 +287,7 @@ bh_traverse3_kernel(const double4 *__restrict__ com, const uint2 *__restrict__ m
             const double4 c = com[item.x];
             kid_lo = reinterpret_cast<const uint4 *>(ctab)[2 * (size_t) item.x];
             kid_hi = reinterpret_cast<const uint4 *>(ctab)[2 * (size_t) item.x + 1];
-            const bool massless = (__double2hiint(c.w) | __double2loint(c.w)) == 0;  // invisible in the reference (:349)
+            const bool massless = STATS && (__double2hiint(c.w) | __double2loint(c.w)) == 0;  // invisible in the reference (:349)
             if (massless) {
                 cls = 0;
             } else if (mt.y & NB_LEAF_FLAG) {

@@ -2,7 +2,7 @@
 //   mandatory  --file --dt --t_end --vs --vs_dir --algorithm=<naive|BarnesHut>
 //   optional   --use_gpus --energy --block_size --opt_stage --theta --num_wi_octree --num_wi_top_octree --num_wi_AABB
 //              --num_wi_com --max_level_top_octree --wg_size_barnes_hut --sort_bodies --storage_size_param
-//              --stack_size_param
+//              --stack_size_param; new: --stream_output (write each snapshot immediately, O(N) host memory)
 // cxxopts (a network FetchContent dependency of the reference) is replaced by the small parser below, which accepts
 // `--key=value`, `--key value` and bare boolean flags.  One process drives one GPU; under torchrun-style launchers
 // (WORLD_SIZE / RANK / LOCAL_RANK) the processes share the bodies and rank 0 writes the output.
@@ -28,8 +28,8 @@ public:
         static const std::set<std::string> known = {
             "file", "dt", "t_end", "vs", "vs_dir", "theta", "num_wi_octree", "num_wi_top_octree", "num_wi_AABB",
             "num_wi_com", "max_level_top_octree", "storage_size_param", "stack_size_param", "block_size", "algorithm",
-            "energy", "sort_bodies", "use_gpus", "wg_size_barnes_hut", "opt_stage"};
-        static const std::set<std::string> booleans = {"energy", "sort_bodies", "use_gpus"};
+            "energy", "sort_bodies", "use_gpus", "wg_size_barnes_hut", "opt_stage", "stream_output"};
+        static const std::set<std::string> booleans = {"energy", "sort_bodies", "use_gpus", "stream_output"};
         for (int i = 1; i < argc; ++i) {
             std::string arg = argv[i];
             if (arg.rfind("--", 0) != 0) throw std::invalid_argument("unexpected argument " + arg);
@@ -161,12 +161,16 @@ int main(int argc, char *argv[]) {
             throw std::invalid_argument("Algorithm must either be <naive> or <BarnesHut>");
         }
 
+        // new, optional: write every snapshot as soon as it is complete instead of keeping all of them in RAM
+        const bool stream = options.count("stream_output") && options.boolean("stream_output");
         if (algorithm == "naive") {
             NaiveAlgorithm run(dt, t_end, visualizationStepWidth, outputDirectoryPath);
+            if (stream) run.enableStreaming(simulationData);
             run.startSimulation(simulationData);
             run.generateParaViewOutput(simulationData);
         } else {
             BarnesHutAlgorithm run(dt, t_end, visualizationStepWidth, outputDirectoryPath);
+            if (stream) run.enableStreaming(simulationData);
             run.startSimulation(simulationData);
             run.generateParaViewOutput(simulationData);
         }

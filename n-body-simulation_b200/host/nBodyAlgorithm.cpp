@@ -124,6 +124,7 @@ void nBodyAlgorithm::runTimeLoop(const SimulationData &d, const std::function<vo
     if (configuration::compute_energy) computeEnergy(currentStep);
     storeAccelerations(currentStep);
     if (isOutputRank()) std::cout << "Finished initial step " << currentStep << std::endl << std::endl;
+    streamStep(currentStep);
 
     time += dt;
     timeSinceLastVisualization += dt;
@@ -164,6 +165,7 @@ void nBodyAlgorithm::runTimeLoop(const SimulationData &d, const std::function<vo
             vx.resize(n); vy.resize(n); vz.resize(n);
             check(nb_get_velocities(ctx, vx.data(), vy.data(), vz.data()), "nb_get_velocities");
             if (configuration::compute_energy) computeEnergy(currentStep);
+            streamStep(currentStep);
             currentStep += 1;
             timeSinceLastVisualization = 0.0;
         }
@@ -197,16 +199,102 @@ const char *const kCloseArray = "</DataArray>";
 
 }  // namespace
 
-void nBodyAlgorithm::generateParaViewOutput(const SimulationData &d) {
-    if (!isOutputRank()) return;
+void nBodyAlgorithm::prepareOutputDirectory() {
+    if (!lastOutputPath.empty()) return;
     // <vs_dir>/<ctime with ' ' -> '_'>/ exactly like the reference (nBodyAlgorithm.cpp:132-140)
     std::time_t now = std::time(nullptr);
     std::string stamp = std::ctime(&now);
     std::replace(stamp.begin(), stamp.end(), ' ', '_');
     stamp.pop_back();  // trailing newline
-    const std::string base = outputDirectory + '/' + stamp + '/';
-    std::filesystem::create_directories(base);
-    lastOutputPath = base;
+    lastOutputPath = outputDirectory + '/' + stamp + '/';
+    std::filesystem::create_directories(lastOutputPath);
+}
+
+void nBodyAlgorithm::writeStepFile(d_type::int_t step, const SimulationData &d) {
+    const bool energy = configuration::compute_energy;
+    std::ofstream f(lastOutputPath + "simulation_step" + std::to_string(step) + ".vtp");
+    const std::vector<double> &px = positions_x[step], &py = positions_y[step], &pz = positions_z[step];
+    const std::vector<double> &vx = velocities_x[step], &vy = velocities_y[step], &vz = velocities_z[step];
+    const std::vector<double> &an = acceleration[step];
+    const std::size_t n = px.size();
+
+    f << "<?xml version=\"1.0\"?>" << '\n'
+      << "<VTKFile type=\"PolyData\" version=\"0.1\" byte_order=\"LittleEndian\" header_type=\"UInt64\">" << '\n'
+      << "<PolyData>" << '\n'
+      << "<Piece NumberOfPoints=\"" << n << "\" NumberOfVerts=\"" << n << "\">" << '\n'
+      << "<Points>" << '\n';
+    openArray(f, "Float64", "position", 3);
+    for (std::size_t j = 0; j < n; ++j) f << px.at(j) << " " << py.at(j) << " " << pz.at(j) << '\n';
+    f << kCloseArray << '\n' << "</Points>" << '\n' << "<PointData>" << '\n';
+
+    openArray(f, "Int32", "body_id", 1);
+    for (std::size_t j = 0; j < n; ++j) f << j << '\n';
+    f << kCloseArray << '\n';
+
+    openArray(f, "Float64", "velocity", 3);
+    for (std::size_t j = 0; j < vx.size(); ++j) f << vx.at(j) << " " << vy.at(j) << " " << vz.at(j) << '\n';
+    f << kCloseArray << '\n';
+
+    openArray(f, "Float64", "acceleration", 1);
+    for (std::size_t j = 0; j < n; ++j) f << an[j] << '\n';
+    f << kCloseArray << '\n';
+
+    openArray(f, "Float64", "mass", 1);
+    for (double m : d.mass) f << m << '\n';
+    f << kCloseArray << '\n';
+
+    // names as space separated ASCII codes terminated by " 0" (nBodyAlgorithm.cpp:344-351)
+    openArray(f, "String", "name", 1);
+    for (const std::string &nm : d.names) {
+        for (char c : nm) f << (int) c << ' ';
+        f << " 0" << '\n';
+    }
+    f << kCloseArray << '\n';
+
+    openArray(f, "Int32", "orbit_class", 1);
+    for (const std::string &c : d.body_classes) f << orbitClassId(c) << '\n';
+    f << kCloseArray << '\n' << "</PointData>" << '\n' << "<Verts>" << '\n';
+
+    f << "<DataArray type=\"Int64\" Name=\"offsets\">" << '\n';
+    for (std::size_t j = 1; j <= n; ++j) f << std::to_string(j) << ' ';
+    f << '\n' << kCloseArray << '\n';
+    f << "<DataArray type=\"Int64\" Name=\"connectivity\">" << '\n';
+    for (std::size_t j = 0; j < n; ++j) f << std::to_string(j) << ' ';
+    f << '\n' << kCloseArray << '\n' << "</Verts>" << '\n' << "</Piece>" << '\n' << "<FieldData>" << '\n';
+
+    // energies are 0 when --energy is off (nBodyAlgorithm.cpp:253-284)
+    openField(f, "kinetic energy");
+    if (energy) f << kineticEnergy[step] << '\n'; else f << 0 << '\n';
+    f << kCloseArray << '\n';
+    openField(f, "potential energy");
+    if (energy) f << potentialEnergy[step] << '\n'; else f << 0 << '\n';
+    f << kCloseArray << '\n';
+    openField(f, "total energy");
+    if (energy) f << totalEnergy[step] << '\n'; else f << 0 << '\n';
+    f << kCloseArray << '\n';
+    openField(f, "virial equilibrium");
+    if (energy) f << virialEquilibrium[step] << '\n'; else f << 0 << '\n';
+    f << kCloseArray << '\n' << "</FieldData>" << '\n' << "</PolyData>" << '\n' << "</VTKFile>" << '\n';
+}
+
+void nBodyAlgorithm::enableStreaming(const SimulationData &d) { streamData = &d; }
+
+void nBodyAlgorithm::streamStep(d_type::int_t step) {
+    if (!streamData || !isOutputRank()) return;
+    prepareOutputDirectory();
+    writeStepFile(step, *streamData);
+    stepsStreamed = step + 1;
+    // keep only what lastState.csv needs, release the rest
+    lastPos_x.swap(positions_x[step]); lastPos_y.swap(positions_y[step]); lastPos_z.swap(positions_z[step]);
+    positions_x.erase(step); positions_y.erase(step); positions_z.erase(step);
+    velocities_x.erase(step); velocities_y.erase(step); velocities_z.erase(step);
+    acceleration.erase(step);
+}
+
+void nBodyAlgorithm::generateParaViewOutput(const SimulationData &d) {
+    if (!isOutputRank()) return;
+    prepareOutputDirectory();
+    const std::string &base = lastOutputPath;
 
     timer.exportJSON(base + "times.json");
     outputLastState(base + "lastState.csv");
@@ -216,82 +304,22 @@ void nBodyAlgorithm::generateParaViewOutput(const SimulationData &d) {
         << "<VTKFile type=\"Collection\" version=\"0.1\" byte_order=\"LittleEndian\" compressor=\"vtkZLibDataCompressor\">"
         << '\n' << "<Collection>" << '\n';
 
-    const bool energy = configuration::compute_energy;
-    for (d_type::int_t step = 0; step < positions_x.size(); ++step) {
+    const d_type::int_t steps = stepsStreamed + (d_type::int_t) positions_x.size();
+    for (d_type::int_t step = 0; step < steps; ++step) {
         const std::string name = "simulation_step" + std::to_string(step) + ".vtp";
         pvd << "<DataSet timestep=\"" << step << "\" group=\"\" part=\"0\" file=\"" << name << "\"/>" << '\n';
-
-        std::ofstream f(base + name);
-        const std::vector<double> &px = positions_x[step], &py = positions_y[step], &pz = positions_z[step];
-        const std::vector<double> &vx = velocities_x[step], &vy = velocities_y[step], &vz = velocities_z[step];
-        const std::vector<double> &an = acceleration[step];
-        const std::size_t n = px.size();
-
-        f << "<?xml version=\"1.0\"?>" << '\n'
-          << "<VTKFile type=\"PolyData\" version=\"0.1\" byte_order=\"LittleEndian\" header_type=\"UInt64\">" << '\n'
-          << "<PolyData>" << '\n'
-          << "<Piece NumberOfPoints=\"" << n << "\" NumberOfVerts=\"" << n << "\">" << '\n'
-          << "<Points>" << '\n';
-        openArray(f, "Float64", "position", 3);
-        for (std::size_t j = 0; j < n; ++j) f << px.at(j) << " " << py.at(j) << " " << pz.at(j) << '\n';
-        f << kCloseArray << '\n' << "</Points>" << '\n' << "<PointData>" << '\n';
-
-        openArray(f, "Int32", "body_id", 1);
-        for (std::size_t j = 0; j < n; ++j) f << j << '\n';
-        f << kCloseArray << '\n';
-
-        openArray(f, "Float64", "velocity", 3);
-        for (std::size_t j = 0; j < vx.size(); ++j) f << vx.at(j) << " " << vy.at(j) << " " << vz.at(j) << '\n';
-        f << kCloseArray << '\n';
-
-        openArray(f, "Float64", "acceleration", 1);
-        for (std::size_t j = 0; j < n; ++j) f << an[j] << '\n';
-        f << kCloseArray << '\n';
-
-        openArray(f, "Float64", "mass", 1);
-        for (double m : d.mass) f << m << '\n';
-        f << kCloseArray << '\n';
-
-        // names as space separated ASCII codes terminated by " 0" (nBodyAlgorithm.cpp:344-351)
-        openArray(f, "String", "name", 1);
-        for (const std::string &nm : d.names) {
-            for (char c : nm) f << (int) c << ' ';
-            f << " 0" << '\n';
-        }
-        f << kCloseArray << '\n';
-
-        openArray(f, "Int32", "orbit_class", 1);
-        for (const std::string &c : d.body_classes) f << orbitClassId(c) << '\n';
-        f << kCloseArray << '\n' << "</PointData>" << '\n' << "<Verts>" << '\n';
-
-        f << "<DataArray type=\"Int64\" Name=\"offsets\">" << '\n';
-        for (std::size_t j = 1; j <= n; ++j) f << std::to_string(j) << ' ';
-        f << '\n' << kCloseArray << '\n';
-        f << "<DataArray type=\"Int64\" Name=\"connectivity\">" << '\n';
-        for (std::size_t j = 0; j < n; ++j) f << std::to_string(j) << ' ';
-        f << '\n' << kCloseArray << '\n' << "</Verts>" << '\n' << "</Piece>" << '\n' << "<FieldData>" << '\n';
-
-        // energies are 0 when --energy is off (nBodyAlgorithm.cpp:253-284)
-        openField(f, "kinetic energy");
-        if (energy) f << kineticEnergy[step] << '\n'; else f << 0 << '\n';
-        f << kCloseArray << '\n';
-        openField(f, "potential energy");
-        if (energy) f << potentialEnergy[step] << '\n'; else f << 0 << '\n';
-        f << kCloseArray << '\n';
-        openField(f, "total energy");
-        if (energy) f << totalEnergy[step] << '\n'; else f << 0 << '\n';
-        f << kCloseArray << '\n';
-        openField(f, "virial equilibrium");
-        if (energy) f << virialEquilibrium[step] << '\n'; else f << 0 << '\n';
-        f << kCloseArray << '\n' << "</FieldData>" << '\n' << "</PolyData>" << '\n' << "</VTKFile>" << '\n';
+        if (step >= stepsStreamed) writeStepFile(step, d);
     }
     pvd << "</Collection>" << '\n' << "</VTKFile>" << '\n';
 }
 
 void nBodyAlgorithm::outputLastState(const std::string &path) {
     std::ofstream csv(path);
-    const d_type::int_t last = positions_x.size() - 1;
     csv << "position_x, position_y, position_z \n";
-    const std::vector<double> &px = positions_x[last], &py = positions_y[last], &pz = positions_z[last];
+    const bool streamed = positions_x.empty();  // streaming mode released the maps and kept the last positions
+    const d_type::int_t last = streamed ? 0 : (d_type::int_t) positions_x.rbegin()->first;
+    const std::vector<double> &px = streamed ? lastPos_x : positions_x[last];
+    const std::vector<double> &py = streamed ? lastPos_y : positions_y[last];
+    const std::vector<double> &pz = streamed ? lastPos_z : positions_z[last];
     for (std::size_t j = 0; j < px.size(); ++j) csv << px.at(j) << "," << py.at(j) << "," << pz.at(j) << '\n';
 }

@@ -40,6 +40,11 @@ public:
     void generateParaViewOutput(const SimulationData &simulationData);
     void outputLastState(const std::string &path);
 
+    // Streaming mode (new, `--stream_output=true`): every visualised step is written as soon as it is
+    // complete and its vectors are released, so host memory stays O(N) instead of O(N * snapshots).  The files are
+    // byte-identical to the ones generateParaViewOutput writes.
+    void enableStreaming(const SimulationData &simulationData);
+
     // energies of the current device state, stored under currentStep (reference nBodyAlgorithm.cpp:11-86)
     void computeEnergy(d_type::int_t currentStep);
     // |a| of the current device accelerations (reference nBodyAlgorithm.cpp:88-102)
@@ -49,6 +54,16 @@ public:
 
     // where generateParaViewOutput wrote its files (empty before the call)
     std::string lastOutputPath;
+
+private:
+    const SimulationData *streamData = nullptr;      // non-null in streaming mode
+    d_type::int_t stepsStreamed = 0;                  // .vtp files already written
+    std::vector<double> lastPos_x, lastPos_y, lastPos_z;
+    void prepareOutputDirectory();
+    void writeStepFile(d_type::int_t step, const SimulationData &simulationData);
+    void streamStep(d_type::int_t step);
+
+public:
     bool isOutputRank() const { return configuration::rank == 0; }
 
 protected:

@@ -100,3 +100,83 @@ def test_config1_full_year_naive(nb, oracle, tmp_path, golden_dir):
         # equal at printed precision (6 significant digits, one unit in the last place of slack)
         assert np.all(np.abs(got - want) <= 1.01e-5 * np.abs(want) + 1e-9)
     assert len([f for f in os.listdir(d) if f.endswith(".vtp")]) == 366
+
+
+# ---- ParaView writer: byte compatibility with the reference's format ----------------------------------------------------
+ORBIT_CLASSES = ["AMO", "APO", "ATE", "IEO", "MCA", "IMB", "MBA", "OMB", "CEN", "TJN", "TNO", "AST", "PAA", "HYA", "STA",
+                 "DWA", "PLA", "SAT"]   # nBodyAlgorithm.cpp:298-342, numbered from 1; anything else -> 0
+
+
+def g(v):
+    """C++ `ostream << double` with the default precision (6 significant digits) == printf %g."""
+    return "%g" % v
+
+
+def expected_vtp(names, classes, m, px, py, pz, vx, vy, vz, anorm, energies=None):
+    """Python restatement of the reference's .vtp layout (nBodyAlgorithm.cpp:156-245, 253-395)."""
+    n = len(px)
+    L = ['<?xml version="1.0"?>',
+         '<VTKFile type="PolyData" version="0.1" byte_order="LittleEndian" header_type="UInt64">', "<PolyData>",
+         '<Piece NumberOfPoints="%d" NumberOfVerts="%d">' % (n, n), "<Points>",
+         '<DataArray type="Float64" Name="position" NumberOfComponents="3" format="ascii">']
+    L += ["%s %s %s" % (g(a), g(b), g(c)) for a, b, c in zip(px, py, pz)]
+    L += ["</DataArray>", "</Points>", "<PointData>",
+          '<DataArray type="Int32" Name="body_id" NumberOfComponents="1" format="ascii">']
+    L += [str(j) for j in range(n)]
+    L += ["</DataArray>", '<DataArray type="Float64" Name="velocity" NumberOfComponents="3" format="ascii">']
+    L += ["%s %s %s" % (g(a), g(b), g(c)) for a, b, c in zip(vx, vy, vz)]
+    L += ["</DataArray>", '<DataArray type="Float64" Name="acceleration" NumberOfComponents="1" format="ascii">']
+    acc_first = len(L)
+    L += [g(a) for a in anorm]
+    acc_last = len(L)
+    L += ["</DataArray>", '<DataArray type="Float64" Name="mass" NumberOfComponents="1" format="ascii">']
+    L += [g(v) for v in m]
+    L += ["</DataArray>", '<DataArray type="String" Name="name" NumberOfComponents="1" format="ascii">']
+    L += ["".join("%d " % ord(ch) for ch in nm) + " 0" for nm in names]
+    L += ["</DataArray>", '<DataArray type="Int32" Name="orbit_class" NumberOfComponents="1" format="ascii">']
+    L += [str(ORBIT_CLASSES.index(c) + 1 if c in ORBIT_CLASSES else 0) for c in classes]
+    L += ["</DataArray>", "</PointData>", "<Verts>", '<DataArray type="Int64" Name="offsets">',
+          "".join("%d " % j for j in range(1, n + 1)), "</DataArray>", '<DataArray type="Int64" Name="connectivity">',
+          "".join("%d " % j for j in range(n)), "</DataArray>", "</Verts>", "</Piece>", "<FieldData>"]
+    e = energies if energies is not None else [0, 0, 0, 0]
+    for name, val in zip(("kinetic energy", "potential energy", "total energy", "virial equilibrium"), e):
+        L += ['<DataArray type="Float64" Name="%s" NumberOfTuples="1" format="ascii">' % name,
+              g(val) if energies is not None else "0", "</DataArray>"]
+    L += ["</FieldData>", "</PolyData>", "</VTKFile>"]
+    return L, (acc_first, acc_last)
+
+
+@pytest.mark.parametrize("stream", [False, True])
+def test_vtp_and_pvd_are_byte_compatible(nb, oracle, tmp_path, golden_dir, stream):
+    fixture = os.path.join(golden_dir, "solar_178.csv")
+    names, classes, m, x, y, z, vx, vy, vz = load_csv(fixture)
+    flags = ["--dt=6h", "--t_end=2d", "--vs=1d", "--algorithm=naive"] + (["--stream_output=true"] if stream else [])
+    d, _ = run_exe(tmp_path, fixture, *flags)
+    ref = oracle.simulate("naive", m, x, y, z, vx, vy, vz, 0.25, 2.0, 1.0)
+    assert ref["n_snap"] == 3
+    pvd = open(os.path.join(d, "simulation.pvd")).read().splitlines()
+    assert pvd[:3] == ['<?xml version="1.0"?>',
+                       '<VTKFile type="Collection" version="0.1" byte_order="LittleEndian" compressor="vtkZLibDataCompressor">',
+                       "<Collection>"]
+    assert pvd[3:6] == ['<DataSet timestep="%d" group="" part="0" file="simulation_step%d.vtp"/>' % (i, i) for i in range(3)]
+    assert pvd[6:] == ["</Collection>", "</VTKFile>"]
+    for step in range(3):
+        got = open(os.path.join(d, "simulation_step%d.vtp" % step)).read().split("\n")
+        assert got[-1] == ""          # file ends with a newline
+        got = got[:-1]
+        want, (a0, a1) = expected_vtp(names, classes, m, ref["px"][step], ref["py"][step], ref["pz"][step],
+                                      ref["vx"][step], ref["vy"][step], ref["vz"][step], ref["anorm"][step])
+        assert len(got) == len(want)
+        if step == 0:
+            # positions / adjusted velocities of step 0 are pure host arithmetic: every byte must match
+            assert got[:a0] == want[:a0] and got[a1:] == want[a1:]
+        else:
+            assert got[a1:] == want[a1:]                      # masses, names, classes, cells, field data
+            assert got[:6] == want[:6]
+        # GPU-computed numbers: equal at the printed precision up to one unit in the last digit
+        for gl, wl in zip(got[:a1], want[:a1]):
+            if gl != wl:
+                gv = np.array(gl.split(), dtype=float); wv = np.array(wl.split(), dtype=float)
+                assert gv.shape == wv.shape and np.all(np.abs(gv - wv) <= 1.01e-5 * np.abs(wv) + 1e-300)
+    last = open(os.path.join(d, "lastState.csv")).read().splitlines()
+    assert last[0] == "position_x, position_y, position_z " and len(last) == 179
