@@ -55,7 +55,7 @@ typedef struct nb_config {
     int32_t opt_stage;           /* naive_algorithm::optimization_stage (:11), 0..2; one kernel serves all */
     int32_t sort_bodies;         /* barnes_hut_algorithm::sortBodies (:21); traversal order only           */
     int32_t wg_size_barnes_hut;  /* barnes_hut_algorithm::workGroupSize (:22) -> traversal CTA size        */
-    int32_t storage_size_param;  /* main.cpp:122-127; accepted, node pool is sized exactly (<= 2N nodes)   */
+    int32_t storage_size_param;  /* main.cpp:122-127; node pool = N + param*N/8 nodes (same budget as the ref.) */
     int32_t stack_size_param;    /* main.cpp:129-134; accepted, traversal is stackless                     */
     int32_t num_wi_aabb;         /* AABBWorkItemCount (:14); result is independent of it (min/max)         */
     int32_t num_wi_octree;       /* accepted, ignored (lock-free build)                                    */
@@ -175,8 +175,8 @@ typedef enum nb_timer {
     NB_T_LEAPFROG1,        /* "Leapfrog Part 1" */
     NB_T_LEAPFROG2,        /* "Leapfrog Part 2" */
     NB_T_AABB,             /* "AABB creation" */
-    NB_T_KEYS_SORT,        /* "Sort bodies for subtrees" (octant keys + radix sort) */
-    NB_T_BUILD,            /* "Build subtrees" (node construction) */
+    NB_T_KEYS_SORT,        /* "Sort bodies for subtrees" (octant keys + radix sort + state reorder) */
+    NB_T_BUILD,            /* "Build subtrees" (node construction + per-depth node lists) */
     NB_T_COM,              /* "Compute center of mass" */
     NB_T_TREE_TOTAL,       /* "Octree creation" */
     NB_T_ENERGY,

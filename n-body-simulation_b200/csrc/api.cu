@@ -22,8 +22,6 @@ int nb_fail(nb_ctx *ctx, int status, const char *fmt, ...) {
     return status;
 }
 
-static thread_local std::string g_create_error;
-
 extern "C" {
 
 int nb_abi_version(void) { return NB_ABI_VERSION; }
@@ -107,7 +105,6 @@ void nb_destroy(nb_ctx *ctx) {
     nb_free(&ctx->anorm); nb_free(&ctx->src); nb_free(&ctx->e_partial); nb_free(&ctx->naive_partial);
     for (int k = 0; k < 10; ++k) nb_free(&ctx->alt[k]);
     nb_free(&ctx->id); nb_free(&ctx->id_alt);
-    if (ctx->h_pinned) cudaFreeHost(ctx->h_pinned);
     for (int i = 0; i < 2 * NB_T_COUNT; ++i) cudaEventDestroy(ctx->ev[i]);
     for (int i = 0; i < 8; ++i) cudaEventDestroy(ctx->user_ev[i]);
     cudaStreamDestroy(ctx->stream);

@@ -31,7 +31,7 @@ struct __align__(16) nb_src_rec {
 struct nb_bh_state {
     // per-body, sorted order
     uint64_t *key_hi = nullptr, *key_lo = nullptr;          // octant-path keys (visit-rank digits)
-    uint64_t *key_hi_alt = nullptr;                          // radix sort ping-pong
+    uint64_t *key_hi_alt = nullptr;                          // radix sort ping-pong; holds the sorted key_lo after the build
     uint32_t *perm = nullptr, *perm_alt = nullptr;           // sorted index -> storage slot before this build's reorder
     int32_t *delta = nullptr;                                // common-prefix digits of sorted neighbours (i, i+1)
     uint32_t *chain_cnt = nullptr, *chain_base = nullptr;    // internal nodes starting at body i, and their scan
@@ -45,15 +45,13 @@ struct nb_bh_state {
     uint32_t *body_count = nullptr;
     // sort scratch
     uint32_t *hist = nullptr;
-    void *scan_tmp = nullptr;
-    size_t scan_tmp_bytes = 0;
     // results
     uint32_t *visits = nullptr;                              // per-body visit counters (stats)
     unsigned long long *stat_totals = nullptr;               // {visits, accepts}
     // device scalars
     double *aabb_dev = nullptr;                              // 7 doubles: min xyz, max xyz, edge
     double *aabb_partial = nullptr;
-    uint32_t *dev_flags = nullptr;                           // [0]=depth overflow flag, [1]=num nodes, [2]=max depth
+    uint32_t *dev_flags = nullptr;                           // [0] error bits (1 depth, 2 pool), [1] internal node count, [2] max depth
     uint64_t cap_bodies = 0, cap_nodes = 0;
     uint64_t num_nodes = 0, num_internal = 0;
     uint32_t max_depth = 0;
@@ -88,9 +86,6 @@ struct nb_ctx {
     size_t naive_partial_cap = 0;
     // energy
     double *e_partial = nullptr;  // 2*n doubles: kinetic, potential per body
-    // host staging (pinned)
-    double *h_pinned = nullptr;
-    size_t h_pinned_bytes = 0;
     nb_bh_state bh;
     // timers
     bool timers_enabled = false;

@@ -180,12 +180,12 @@ def t_perf_bh():
     section("perf bh")
     for gen, n, theta in (("plummer", 1 << 20, 0.5), ("uniform_sphere", 1 << 22, 0.5), ("uniform_sphere", 1 << 24, 0.5)):
         m, x, y, z, vx, vy, vz = getattr(nb.generators, gen)(n, seed=1)
-        for single in (1, 0):
+        for single in (0, 3):
             for wg in (64, 128, 256):
                 c = nb.Context(theta=theta, wg_size_barnes_hut=wg, single_phase_walk=single); c.set_bodies(m, x, y, z, vx, vy, vz); c.enable_timers(True)
                 c.bh_build(); c.bh_accel(); c.synchronize()
                 c.bh_build(); c.bh_accel(); t = c.timers(); info = c.bh_tree_info()
-                print(gen, n, "single" if single else "two-phase", "wg", wg, "depth", info.max_depth, {k: round(v, 3) for k, v in t.items() if v}, flush=True)
+                print(gen, n, "walk" if single == 0 else "group", "wg", wg, "depth", info.max_depth, {k: round(v, 3) for k, v in t.items() if v}, flush=True)
                 c.close()
 
 
