@@ -11,8 +11,9 @@
 //   * centre of mass = sum over children in octant order 0..7 of (m*x, m*y, m*z, m).
 //
 // B200-first construction (lock-free, O(N) work, no host round trips):
-//   1. every body descends the cube arithmetically (exactly the reference's fp64 compares) and records its path as
-//      2 x 63-bit keys, 3 bits per level, 42 levels.  The digit is the octant's VISIT RANK 4u+2b+(1-r) in the
+//   1. every body descends the cube arithmetically (exactly the reference's fp64 compares) and records its path as a
+//      63-bit key, 3 bits per level, 21 levels; a second key word (levels 21..41) is computed only for the rare bodies
+//      that share all 21 upper levels with a neighbour (closer than edge*2^-21).  The digit is the octant's VISIT RANK 4u+2b+(1-r) in the
 //      reference's traversal order [2,0,3,1,6,4,7,5] (BarnesHutAlgorithm.cpp:370-385), so sorted order == DFS order.
 //   2. stable LSD radix sort of (key_hi, slot) (scan_sort.cuh); rare equal-key_hi runs are ordered by key_lo; then the
 //      whole body state (m, x, v, a, id) is physically permuted into the sorted order, so everything downstream streams
@@ -110,45 +111,53 @@ aabb_final_kernel(const double *__restrict__ partial, int n_partials, double *__
 }
 
 // ---- 2. octant-path keys --------------------------------------------------------------------------------------------
-// Descent test of ParallelOctreeTopDownSubtrees.cpp:400-406 with the child bounds of :256-315.
-__global__ void __launch_bounds__(256)
-keys_kernel(const double *__restrict__ x, const double *__restrict__ y, const double *__restrict__ z, uint64_t n,
-            const double *__restrict__ aabb, uint64_t *__restrict__ key_hi, uint64_t *__restrict__ key_lo) {
-    const uint64_t i = (uint64_t) blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    const double px = x[i], py = y[i], pz = z[i];
-    double mnx = aabb[0], mny = aabb[1], mnz = aabb[2], edge = aabb[6];
-    uint64_t hi = 0, lo = 0;
-#pragma unroll 1
-    for (int half = 0; half < 2; ++half) {
-        uint64_t k = 0;
+// Descent test of ParallelOctreeTopDownSubtrees.cpp:400-406 with the child bounds of :256-315.  One call advances the
+// cell (mn*, edge) by 21 levels and returns the 63-bit key word of those levels.
+__device__ __forceinline__ uint64_t descend21(double px, double py, double pz, double &mnx, double &mny, double &mnz,
+                                             double &edge) {
+    uint64_t k = 0;
 #pragma unroll
-        for (int l = 0; l < 21; ++l) {
-            const double h = __dmul_rn(edge, 0.5);           // parentEdgeLength / 2 (exact halving)
-            const double midx = __dadd_rn(mnx, h);
-            const double midy = __dadd_rn(mny, h);
-            const double midz = __dadd_rn(mnz, h);
-            const bool upper = py > midy;
-            const bool right = px > midx;
-            const bool back = pz < midz;
-            // visit-rank digit: 4u + 2b + (1-r)
-            const uint64_t digit = (upper ? 4u : 0u) | (back ? 2u : 0u) | (right ? 0u : 1u);
-            k = (k << 3) | digit;
-            mny = upper ? midy : mny;
-            mnx = right ? midx : mnx;
-            mnz = back ? mnz : midz;                         // z gets +h when back == 0 (:256-315)
-            edge = h;
-        }
-        if (half == 0) hi = k; else lo = k;
+    for (int l = 0; l < 21; ++l) {
+        const double h = __dmul_rn(edge, 0.5);           // parentEdgeLength / 2 (exact halving)
+        const double midx = __dadd_rn(mnx, h);
+        const double midy = __dadd_rn(mny, h);
+        const double midz = __dadd_rn(mnz, h);
+        const bool upper = py > midy;
+        const bool right = px > midx;
+        const bool back = pz < midz;
+        // visit-rank digit: 4u + 2b + (1-r)
+        const uint64_t digit = (upper ? 4u : 0u) | (back ? 2u : 0u) | (right ? 0u : 1u);
+        k = (k << 3) | digit;
+        mny = upper ? midy : mny;
+        mnx = right ? midx : mnx;
+        mnz = back ? mnz : midz;                         // z gets +h when back == 0 (:256-315)
+        edge = h;
     }
-    key_hi[i] = hi;
-    key_lo[i] = lo;
+    return k;
 }
 
-// ---- 2b. order equal-key_hi runs by key_lo (bodies closer than edge * 2^-21) -----------------------------------------
+// levels 0..20 of every body (the sort key)
 __global__ void __launch_bounds__(256)
-fix_ties_kernel(const uint64_t *__restrict__ hi_sorted, const uint64_t *__restrict__ key_lo, uint32_t *__restrict__ perm,
-                uint64_t n, uint32_t *__restrict__ flags) {
+keys_kernel(const double *__restrict__ x, const double *__restrict__ y, const double *__restrict__ z, uint64_t n,
+            const double *__restrict__ aabb, uint64_t *__restrict__ key_hi) {
+    const uint64_t i = (uint64_t) blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    double mnx = aabb[0], mny = aabb[1], mnz = aabb[2], edge = aabb[6];
+    key_hi[i] = descend21(x[i], y[i], z[i], mnx, mny, mnz, edge);
+}
+
+// levels 21..41, only ever needed for bodies that share all 21 upper levels with a neighbour (closer than edge*2^-21)
+__device__ __forceinline__ uint64_t key_lo_of(double px, double py, double pz, const double *__restrict__ aabb) {
+    double mnx = aabb[0], mny = aabb[1], mnz = aabb[2], edge = aabb[6];
+    descend21(px, py, pz, mnx, mny, mnz, edge);
+    return descend21(px, py, pz, mnx, mny, mnz, edge);
+}
+
+// ---- 2b. order equal-key_hi runs by the lower key word ---------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+fix_ties_kernel(const uint64_t *__restrict__ hi_sorted, const double *__restrict__ x, const double *__restrict__ y,
+                const double *__restrict__ z, const double *__restrict__ aabb, uint32_t *__restrict__ perm, uint64_t n,
+                uint32_t *__restrict__ flags) {
     const uint64_t i = (uint64_t) blockIdx.x * blockDim.x + threadIdx.x;
     if (i + 1 >= n) return;
     const uint64_t k = hi_sorted[i];
@@ -156,13 +165,13 @@ fix_ties_kernel(const uint64_t *__restrict__ hi_sorted, const uint64_t *__restri
     if (i > 0 && hi_sorted[i - 1] == k) return;
     uint64_t e = i + 1;
     while (e + 1 < n && hi_sorted[e + 1] == k) ++e;
-    for (uint64_t a = i + 1; a <= e; ++a) {  // insertion sort of the run by key_lo
+    for (uint64_t a = i + 1; a <= e; ++a) {  // insertion sort of the run by the lower key word
         const uint32_t pa = perm[a];
-        const uint64_t la = key_lo[pa];
+        const uint64_t la = key_lo_of(x[pa], y[pa], z[pa], aabb);
         uint64_t b = a;
         while (b > i) {
             const uint32_t pb = perm[b - 1];
-            const uint64_t lb = key_lo[pb];
+            const uint64_t lb = key_lo_of(x[pb], y[pb], z[pb], aabb);
             if (lb == la) atomicOr(&flags[0], NB_FLAG_DEPTH);  // identical 42-level paths: coincident bodies
             if (lb <= la) break;
             perm[b] = pb;
@@ -172,6 +181,17 @@ fix_ties_kernel(const uint64_t *__restrict__ hi_sorted, const uint64_t *__restri
     }
 }
 
+// lower key word in sorted order: computed where a neighbour shares the upper word, 0 elsewhere (never consulted there)
+__global__ void __launch_bounds__(256)
+keys_lo_kernel(const uint64_t *__restrict__ hi_sorted, const double *__restrict__ x, const double *__restrict__ y,
+               const double *__restrict__ z, const double *__restrict__ aabb, uint64_t n, uint64_t *__restrict__ lo_sorted) {
+    const uint64_t i = (uint64_t) blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const uint64_t k = hi_sorted[i];
+    const bool tied = (i > 0 && hi_sorted[i - 1] == k) || (i + 1 < n && hi_sorted[i + 1] == k);
+    lo_sorted[i] = tied ? key_lo_of(x[i], y[i], z[i], aabb) : 0ull;
+}
+
 // ---- 3. physical reorder of the whole state into sorted order ----------------------------------------------------------------
 struct reorder_args {
     const double *src[10];
@@ -179,15 +199,13 @@ struct reorder_args {
 };
 __global__ void __launch_bounds__(256)
 reorder_kernel(const uint32_t *__restrict__ perm, uint64_t n, reorder_args a, const uint32_t *__restrict__ id_in,
-               uint32_t *__restrict__ id_out, int identity, const uint64_t *__restrict__ key_lo,
-               uint64_t *__restrict__ lo_sorted) {
+               uint32_t *__restrict__ id_out, int identity) {
     const uint64_t i = (uint64_t) blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     const uint32_t p = perm[i];
 #pragma unroll
     for (int k = 0; k < 10; ++k) a.dst[k][i] = a.src[k][p];
     id_out[i] = identity ? p : id_in[p];
-    lo_sorted[i] = key_lo[p];
 }
 
 // read-back / upload helpers between storage order and body-id order
@@ -238,11 +256,17 @@ delta_kernel(const uint64_t *__restrict__ hi, const uint64_t *__restrict__ lo, u
         cnt[i] = d_cur > d_prev ? (uint32_t) (d_cur - d_prev) : 0u;
         if (d_cur >= NB_MAX_TREE_DEPTH) atomicOr(&flags[0], NB_FLAG_DEPTH);
     }
-    // max depth of the tree = deepest leaf = max(delta) + 1
+    // max depth of the tree = deepest leaf = max(delta) + 1: one atomic per block, and only when it raises the value
+    __shared__ int smax;
+    if (threadIdx.x == 0) smax = -1;
+    __syncthreads();
     int mx = d_cur;
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) mx = max(mx, __shfl_xor_sync(0xffffffffu, mx, o));
-    if ((threadIdx.x & 31) == 0 && mx >= 0) atomicMax(&flags[2], (uint32_t) (mx + 1));
+    if ((threadIdx.x & 31) == 0 && mx >= 0) atomicMax(&smax, mx);
+    __syncthreads();
+    if (threadIdx.x == 0 && smax >= 0 && (uint32_t) (smax + 1) > *(volatile uint32_t *) &flags[2])
+        atomicMax(&flags[2], (uint32_t) (smax + 1));
 }
 
 // ---- 4. node emission ---------------------------------------------------------------------------------------------------
@@ -437,7 +461,6 @@ int nbk_bh_reserve(nb_ctx *ctx) {
     nbk_bh_release(ctx);
     const uint64_t nb = n + 32;
     NB_CHECK(nb_alloc(ctx, &b.key_hi, nb));
-    NB_CHECK(nb_alloc(ctx, &b.key_lo, nb));
     NB_CHECK(nb_alloc(ctx, &b.key_hi_alt, nb));
     NB_CHECK(nb_alloc(ctx, &b.perm, nb));
     NB_CHECK(nb_alloc(ctx, &b.perm_alt, nb));
@@ -467,7 +490,7 @@ int nbk_bh_reserve(nb_ctx *ctx) {
 
 void nbk_bh_release(nb_ctx *ctx) {
     nb_bh_state &b = ctx->bh;
-    nb_free(&b.key_hi); nb_free(&b.key_lo); nb_free(&b.key_hi_alt); nb_free(&b.perm); nb_free(&b.perm_alt);
+    nb_free(&b.key_hi); nb_free(&b.key_hi_alt); nb_free(&b.perm); nb_free(&b.perm_alt);
     nb_free(&b.delta); nb_free(&b.chain_cnt);
     nb_free(&b.chain_base); nb_free(&b.leaf_node); 
     nb_free(&b.visits); nb_free(&b.com); nb_free(&b.msum); nb_free(&b.meta); nb_free(&b.level); nb_free(&b.level_list); nb_free(&b.ctab); 
@@ -508,29 +531,32 @@ int nbk_bh_build(nb_ctx *ctx) {
     uint32_t *perm_sorted = nullptr;
     {
         nb_timer_scope t(ctx, NB_T_KEYS_SORT);
-        keys_kernel<<<g256, 256, 0, ctx->stream>>>(ctx->x, ctx->y, ctx->z, n, b.aabb_dev, b.key_hi, b.key_lo);
+        keys_kernel<<<g256, 256, 0, ctx->stream>>>(ctx->x, ctx->y, ctx->z, n, b.aabb_dev, b.key_hi);
         NB_LAUNCH_CHECK(ctx);
         NB_CHECK(nbprim::radix_sort_pairs(ctx, b.key_hi, b.perm, b.key_hi_alt, b.perm_alt, n, 63, b.hist, &hi_sorted,
                                           &perm_sorted, true));
-        fix_ties_kernel<<<g256, 256, 0, ctx->stream>>>(hi_sorted, b.key_lo, perm_sorted, n, b.dev_flags);
+        fix_ties_kernel<<<g256, 256, 0, ctx->stream>>>(hi_sorted, ctx->x, ctx->y, ctx->z, b.aabb_dev, perm_sorted, n,
+                                                       b.dev_flags);
         NB_LAUNCH_CHECK(ctx);
         // key_hi_alt / perm_alt are reused below: make the sorted data live in (key_hi, perm)
         if (hi_sorted != b.key_hi) {
             uint64_t *tk = b.key_hi; b.key_hi = b.key_hi_alt; b.key_hi_alt = tk;
             uint32_t *tp = b.perm; b.perm = b.perm_alt; b.perm_alt = tp;
         }
-        // move the whole state (and key_lo -> key_hi_alt) into sorted order; the arrays swap roles with their partners
+        // move the whole state into sorted order; the arrays swap roles with their partners
         {
             double **cur[10] = {&ctx->m, &ctx->x, &ctx->y, &ctx->z, &ctx->vx, &ctx->vy, &ctx->vz, &ctx->ax, &ctx->ay, &ctx->az};
             reorder_args ra;
             for (int k = 0; k < 10; ++k) { ra.src[k] = *cur[k]; ra.dst[k] = ctx->alt[k]; }
-            reorder_kernel<<<g256, 256, 0, ctx->stream>>>(b.perm, n, ra, ctx->id, ctx->id_alt, ctx->identity_order ? 1 : 0,
-                                                          b.key_lo, b.key_hi_alt);
+            reorder_kernel<<<g256, 256, 0, ctx->stream>>>(b.perm, n, ra, ctx->id, ctx->id_alt, ctx->identity_order ? 1 : 0);
             NB_LAUNCH_CHECK(ctx);
             for (int k = 0; k < 10; ++k) { double *t = *cur[k]; *cur[k] = ctx->alt[k]; ctx->alt[k] = t; }
             uint32_t *ti = ctx->id; ctx->id = ctx->id_alt; ctx->id_alt = ti;
             ctx->identity_order = false;
         }
+        // lower key word (levels 21..41) of the sorted bodies, where needed (key_hi_alt is free after the sort)
+        keys_lo_kernel<<<g256, 256, 0, ctx->stream>>>(b.key_hi, ctx->x, ctx->y, ctx->z, b.aabb_dev, n, b.key_hi_alt);
+        NB_LAUNCH_CHECK(ctx);
     }
     const uint64_t *hi = b.key_hi, *lo = b.key_hi_alt;
     {

@@ -30,8 +30,8 @@ struct __align__(16) nb_src_rec {
 
 struct nb_bh_state {
     // per-body, sorted order
-    uint64_t *key_hi = nullptr, *key_lo = nullptr;          // octant-path keys (visit-rank digits)
-    uint64_t *key_hi_alt = nullptr;                          // radix sort ping-pong; holds the sorted key_lo after the build
+    uint64_t *key_hi = nullptr;                              // octant-path key, levels 0..20 (visit-rank digits)
+    uint64_t *key_hi_alt = nullptr;                          // radix sort ping-pong; after the sort: key word of levels 21..41 (where needed)
     uint32_t *perm = nullptr, *perm_alt = nullptr;           // sorted index -> storage slot before this build's reorder
     int32_t *delta = nullptr;                                // common-prefix digits of sorted neighbours (i, i+1)
     uint32_t *chain_cnt = nullptr, *chain_base = nullptr;    // internal nodes starting at body i, and their scan
