@@ -19,7 +19,7 @@ NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", 
               "-ccbin", HOST_CXX, "--expt-relaxed-constexpr"]
 
 CU_SOURCES = ["api.cu", "naive.cu", "integrator.cu", "energy.cu", "bh_build.cu", "bh_traverse.cu", "comm.cu", "util.cu"]
-HOST_SOURCES = ["main.cpp", "Configuration.cpp", "InputParser.cpp", "TimeConverter.cpp", "TimeMeasurement.cpp",
+HOST_SOURCES = ["main.cpp", "Configuration.cpp", "InputParser.cpp", "StateFile.cpp", "TimeConverter.cpp", "TimeMeasurement.cpp",
                 "nBodyAlgorithm.cpp", "NaiveAlgorithm.cpp", "BarnesHutAlgorithm.cpp"]
 
 

@@ -108,3 +108,44 @@ def solar_like(n=178, seed=3):
     vx[0] = vy[0] = vz[0] = 0.0
     m[0] = M_SUN
     return m, x, y, z, vx, vy, vz
+
+
+# ---- binary body-state files (host/StateFile.hpp) ---------------------------------------------------------------------
+STATE_MAGIC = b"NBSTATE1"
+
+
+def write_state(path, m, x, y, z, vx, vy, vz, time=0.0, names=None, classes=None):
+    """Writes the bodies as the binary SoA state file `N_Body_Simulation --file=` accepts (no CSV round trip)."""
+    import struct
+    arrays = [np.ascontiguousarray(a, dtype="<f8") for a in (m, x, y, z, vx, vy, vz)]
+    n = arrays[0].size
+    if any(a.size != n for a in arrays):
+        raise ValueError("state arrays differ in length")
+    table = names is not None and classes is not None and n > 0
+    with open(path, "wb") as f:
+        f.write(struct.pack("<8sIIQd32x", STATE_MAGIC, 1, 1 if table else 0, n, float(time)))
+        for a in arrays:
+            f.write(a.tobytes())
+        if table:
+            for nm, cl in zip(names, classes):
+                f.write(nm.encode() + b"\0" + cl.encode() + b"\0")
+
+
+def read_state(path):
+    """-> dict(m, x, y, z, vx, vy, vz, time, names, classes) of a binary state file / checkpoint."""
+    import struct
+    with open(path, "rb") as f:
+        magic, version, flags, n, time = struct.unpack("<8sIIQd32x", f.read(64))
+        if magic != STATE_MAGIC or version != 1:
+            raise ValueError("not a version-1 body-state file: %s" % path)
+        out = {"time": time}
+        for k in ("m", "x", "y", "z", "vx", "vy", "vz"):
+            out[k] = np.frombuffer(f.read(8 * n), dtype="<f8").copy()
+            if out[k].size != n:
+                raise ValueError("state file is truncated: %s" % path)
+        out["names"], out["classes"] = None, None
+        if flags & 1:
+            fields = f.read().split(b"\0")
+            out["names"] = [b.decode() for b in fields[0:2 * n:2]]
+            out["classes"] = [b.decode() for b in fields[1:2 * n:2]]
+    return out

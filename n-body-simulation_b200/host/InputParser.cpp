@@ -1,9 +1,15 @@
 #include "InputParser.hpp"
 
+#include "StateFile.hpp"
+
 #include <fstream>
 #include <stdexcept>
 
 void InputParser::parse_input(std::string &path, SimulationData &d) {
+    if (StateFile::isStateFile(path)) {  // binary SoA state / checkpoint, recognised by its magic
+        StateFile::read(path, d, &d.start_time);
+        return;
+    }
     std::ifstream in(path);
     if (!in) throw std::invalid_argument("cannot open input file " + path);
     std::string line;

@@ -1,5 +1,6 @@
 // CSV reader (reference src/simulationData/InputParser.hpp:17-23, InputParser.cpp:7-51).
 // Format: id,name,class,mass[kg],pos_x,pos_y,pos_z[AU],vel_x,vel_y,vel_z[AU/day]; first line is a header.
+// New: a file starting with the StateFile magic is read as a binary SoA state instead (host/StateFile.hpp).
 #pragma once
 #include <string>
 #include <vector>

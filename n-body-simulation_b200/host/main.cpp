@@ -2,7 +2,9 @@
 //   mandatory  --file --dt --t_end --vs --vs_dir --algorithm=<naive|BarnesHut>
 //   optional   --use_gpus --energy --block_size --opt_stage --theta --num_wi_octree --num_wi_top_octree --num_wi_AABB
 //              --num_wi_com --max_level_top_octree --wg_size_barnes_hut --sort_bodies --storage_size_param
-//              --stack_size_param; new: --stream_output (write each snapshot immediately, O(N) host memory)
+//              --stack_size_param
+//   new        --stream_output (write each snapshot immediately, O(N) host memory), --vtp_format=<ascii|binary>,
+//              --checkpoint=<path> [--checkpoint_every_vs] (binary state for resuming; --file accepts such a state)
 // cxxopts (a network FetchContent dependency of the reference) is replaced by the small parser below, which accepts
 // `--key=value`, `--key value` and bare boolean flags.  One process drives one GPU; under torchrun-style launchers
 // (WORLD_SIZE / RANK / LOCAL_RANK) the processes share the bodies and rank 0 writes the output.
@@ -28,8 +30,10 @@ public:
         static const std::set<std::string> known = {
             "file", "dt", "t_end", "vs", "vs_dir", "theta", "num_wi_octree", "num_wi_top_octree", "num_wi_AABB",
             "num_wi_com", "max_level_top_octree", "storage_size_param", "stack_size_param", "block_size", "algorithm",
-            "energy", "sort_bodies", "use_gpus", "wg_size_barnes_hut", "opt_stage", "stream_output"};
-        static const std::set<std::string> booleans = {"energy", "sort_bodies", "use_gpus", "stream_output"};
+            "energy", "sort_bodies", "use_gpus", "wg_size_barnes_hut", "opt_stage", "stream_output", "vtp_format",
+            "checkpoint", "checkpoint_every_vs"};
+        static const std::set<std::string> booleans = {"energy", "sort_bodies", "use_gpus", "stream_output",
+                                                       "checkpoint_every_vs"};
         for (int i = 1; i < argc; ++i) {
             std::string arg = argv[i];
             if (arg.rfind("--", 0) != 0) throw std::invalid_argument("unexpected argument " + arg);
@@ -163,16 +167,27 @@ int main(int argc, char *argv[]) {
 
         // new, optional: write every snapshot as soon as it is complete instead of keeping all of them in RAM
         const bool stream = options.count("stream_output") && options.boolean("stream_output");
+        bool binaryVtp = false;
+        if (options.count("vtp_format")) {
+            const std::string &format = options.str("vtp_format");
+            if (format != "ascii" && format != "binary") throw std::invalid_argument("vtp_format must either be <ascii> or <binary>");
+            binaryVtp = format == "binary";
+        }
+        const std::string checkpoint = options.count("checkpoint") ? options.str("checkpoint") : std::string();
+        const bool checkpointEveryVs = options.count("checkpoint_every_vs") && options.boolean("checkpoint_every_vs");
+        auto simulate = [&](nBodyAlgorithm &run) {
+            if (stream) run.enableStreaming(simulationData);
+            run.setBinaryOutput(binaryVtp);
+            run.setCheckpoint(checkpoint, checkpointEveryVs);
+            run.startSimulation(simulationData);
+            run.generateParaViewOutput(simulationData);
+        };
         if (algorithm == "naive") {
             NaiveAlgorithm run(dt, t_end, visualizationStepWidth, outputDirectoryPath);
-            if (stream) run.enableStreaming(simulationData);
-            run.startSimulation(simulationData);
-            run.generateParaViewOutput(simulationData);
+            simulate(run);
         } else {
             BarnesHutAlgorithm run(dt, t_end, visualizationStepWidth, outputDirectoryPath);
-            if (stream) run.enableStreaming(simulationData);
-            run.startSimulation(simulationData);
-            run.generateParaViewOutput(simulationData);
+            simulate(run);
         }
     } catch (const std::exception &e) {
         std::cerr << "terminate called after throwing: " << e.what() << std::endl;

@@ -1,5 +1,7 @@
 #include "nBodyAlgorithm.hpp"
 
+#include "StateFile.hpp"
+
 #include <unistd.h>
 
 #include <algorithm>
@@ -131,6 +133,7 @@ void nBodyAlgorithm::runTimeLoop(const SimulationData &d, const std::function<vo
     currentStep += 1;
 
     double ms[NB_T_COUNT];
+    double completedTime = 0.0;  // simulated time of the last finished step
     bool kickPending = false;  // second half-kick of the previous (non-visualised) step still to be applied
     while (time <= t_end + 0.000001) {
         const bool visualizeCurrentStep = std::abs(timeSinceLastVisualization - visualizationStepWidth) < 0.000001;
@@ -165,14 +168,42 @@ void nBodyAlgorithm::runTimeLoop(const SimulationData &d, const std::function<vo
             vx.resize(n); vy.resize(n); vz.resize(n);
             check(nb_get_velocities(ctx, vx.data(), vy.data(), vz.data()), "nb_get_velocities");
             if (configuration::compute_energy) computeEnergy(currentStep);
+            if (checkpointEveryVisualizedStep && !checkpointPath.empty()) {
+                const std::vector<double> *pos[3] = {&positions_x[currentStep], &positions_y[currentStep], &positions_z[currentStep]};
+                const std::vector<double> *vel[3] = {&vx, &vy, &vz};
+                writeCheckpoint(d, d.start_time + time, pos, vel);
+            }
             streamStep(currentStep);
             currentStep += 1;
             timeSinceLastVisualization = 0.0;
         }
+        completedTime = time;
         time += dt;
         timeSinceLastVisualization += dt;
     }
     check(nb_synchronize(ctx), "nb_synchronize");
+    // the last step always closes with its half-kick, so the device holds a complete (x, v) state here
+    if (!checkpointPath.empty()) writeCheckpoint(d, d.start_time + completedTime, nullptr, nullptr);
+}
+
+void nBodyAlgorithm::writeCheckpoint(const SimulationData &d, double time, const std::vector<double> *pos[3],
+                                     const std::vector<double> *vel[3]) {
+    const std::size_t n = configuration::numberOfBodies;
+    std::vector<double> fetched[6];
+    const double *arrays[7] = {d.mass.data(), nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+    if (pos && vel) {
+        for (int k = 0; k < 3; ++k) {
+            arrays[1 + k] = pos[k]->data();
+            arrays[4 + k] = vel[k]->data();
+        }
+    } else {
+        for (auto &v : fetched) v.resize(n);
+        check(nb_get_positions(ctx, fetched[0].data(), fetched[1].data(), fetched[2].data()), "nb_get_positions");
+        check(nb_get_velocities(ctx, fetched[3].data(), fetched[4].data(), fetched[5].data()), "nb_get_velocities");
+        for (int k = 0; k < 6; ++k) arrays[1 + k] = fetched[k].data();
+    }
+    if (!isOutputRank()) return;  // every rank holds the full state; one writes it
+    StateFile::writeArrays(checkpointPath, n, arrays, d.names, d.body_classes, time);
 }
 
 // ---- output ------------------------------------------------------------------------------------------------------
@@ -211,6 +242,7 @@ void nBodyAlgorithm::prepareOutputDirectory() {
 }
 
 void nBodyAlgorithm::writeStepFile(d_type::int_t step, const SimulationData &d) {
+    if (binaryOutput) return writeStepFileBinary(step, d);
     const bool energy = configuration::compute_energy;
     std::ofstream f(lastOutputPath + "simulation_step" + std::to_string(step) + ".vtp");
     const std::vector<double> &px = positions_x[step], &py = positions_y[step], &pz = positions_z[step];
@@ -244,15 +276,18 @@ void nBodyAlgorithm::writeStepFile(d_type::int_t step, const SimulationData &d) 
     f << kCloseArray << '\n';
 
     // names as space separated ASCII codes terminated by " 0" (nBodyAlgorithm.cpp:344-351)
+    // (bodies read from a binary state file may carry no names / classes: empty name, class 0)
     openArray(f, "String", "name", 1);
     for (const std::string &nm : d.names) {
         for (char c : nm) f << (int) c << ' ';
         f << " 0" << '\n';
     }
+    for (std::size_t j = d.names.size(); j < n; ++j) f << " 0" << '\n';
     f << kCloseArray << '\n';
 
     openArray(f, "Int32", "orbit_class", 1);
     for (const std::string &c : d.body_classes) f << orbitClassId(c) << '\n';
+    for (std::size_t j = d.body_classes.size(); j < n; ++j) f << 0 << '\n';
     f << kCloseArray << '\n' << "</PointData>" << '\n' << "<Verts>" << '\n';
 
     f << "<DataArray type=\"Int64\" Name=\"offsets\">" << '\n';
@@ -275,6 +310,91 @@ void nBodyAlgorithm::writeStepFile(d_type::int_t step, const SimulationData &d) 
     openField(f, "virial equilibrium");
     if (energy) f << virialEquilibrium[step] << '\n'; else f << 0 << '\n';
     f << kCloseArray << '\n' << "</FieldData>" << '\n' << "</PolyData>" << '\n' << "</VTKFile>" << '\n';
+}
+
+// Same PolyData as writeStepFile, with every per-body array as an "appended raw" block: after the '_' marker each block
+// is a UInt64 byte count followed by the little-endian values; `offset` counts bytes from the marker.  The name array is
+// omitted (VTK has no binary string arrays); everything else keeps its name, type and component count.
+void nBodyAlgorithm::writeStepFileBinary(d_type::int_t step, const SimulationData &d) {
+    const bool energy = configuration::compute_energy;
+    std::ofstream f(lastOutputPath + "simulation_step" + std::to_string(step) + ".vtp", std::ios::binary);
+    const std::vector<double> &px = positions_x[step], &py = positions_y[step], &pz = positions_z[step];
+    const std::vector<double> &vx = velocities_x[step], &vy = velocities_y[step], &vz = velocities_z[step];
+    const std::vector<double> &an = acceleration[step];
+    const std::uint64_t n = px.size();
+
+    std::uint64_t offset = 0;
+    auto declare = [&](const char *type, const char *name, int components, std::uint64_t bytes) {
+        f << "<DataArray type=\"" << type << "\" Name=\"" << name << "\"";
+        if (components) f << " NumberOfComponents=\"" << components << "\"";
+        f << " format=\"appended\" offset=\"" << offset << "\"/>" << '\n';
+        offset += 8 + bytes;
+    };
+    f << "<?xml version=\"1.0\"?>" << '\n'
+      << "<VTKFile type=\"PolyData\" version=\"0.1\" byte_order=\"LittleEndian\" header_type=\"UInt64\">" << '\n'
+      << "<PolyData>" << '\n'
+      << "<Piece NumberOfPoints=\"" << n << "\" NumberOfVerts=\"" << n << "\">" << '\n'
+      << "<Points>" << '\n';
+    declare("Float64", "position", 3, 24 * n);
+    f << "</Points>" << '\n' << "<PointData>" << '\n';
+    declare("Int32", "body_id", 1, 4 * n);
+    declare("Float64", "velocity", 3, 24 * n);
+    declare("Float64", "acceleration", 1, 8 * n);
+    declare("Float64", "mass", 1, 8 * n);
+    declare("Int32", "orbit_class", 1, 4 * n);
+    f << "</PointData>" << '\n' << "<Verts>" << '\n';
+    declare("Int64", "offsets", 0, 8 * n);
+    declare("Int64", "connectivity", 0, 8 * n);
+    f << "</Verts>" << '\n' << "</Piece>" << '\n' << "<FieldData>" << '\n';
+    f.precision(17);
+    const std::pair<const char *, double> fields[4] = {
+        {"kinetic energy", energy ? kineticEnergy[step] : 0.0}, {"potential energy", energy ? potentialEnergy[step] : 0.0},
+        {"total energy", energy ? totalEnergy[step] : 0.0}, {"virial equilibrium", energy ? virialEquilibrium[step] : 0.0}};
+    for (const auto &field : fields) {
+        openField(f, field.first);
+        f << field.second << '\n' << kCloseArray << '\n';
+    }
+    f << "</FieldData>" << '\n' << "</PolyData>" << '\n' << "<AppendedData encoding=\"raw\">" << '\n' << "_";
+
+    // blocks, in declaration order; large arrays go through a bounded staging buffer
+    constexpr std::uint64_t kChunk = 1 << 16;
+    std::vector<double> stage(3 * kChunk);
+    auto blockHeader = [&](std::uint64_t bytes) { f.write(reinterpret_cast<const char *>(&bytes), 8); };
+    auto interleaved = [&](const std::vector<double> &a, const std::vector<double> &b, const std::vector<double> &c) {
+        blockHeader(24 * n);
+        for (std::uint64_t base = 0; base < n; base += kChunk) {
+            const std::uint64_t m = std::min(kChunk, n - base);
+            for (std::uint64_t j = 0; j < m; ++j) {
+                stage[3 * j] = a[base + j];
+                stage[3 * j + 1] = b[base + j];
+                stage[3 * j + 2] = c[base + j];
+            }
+            f.write(reinterpret_cast<const char *>(stage.data()), (std::streamsize) (24 * m));
+        }
+    };
+    auto generated = [&](auto value, auto make) {  // value: element type tag, make(j) -> element
+        using T = decltype(value);
+        blockHeader(sizeof(T) * n);
+        T *buf = reinterpret_cast<T *>(stage.data());
+        for (std::uint64_t base = 0; base < n; base += kChunk) {
+            const std::uint64_t m = std::min(kChunk, n - base);
+            for (std::uint64_t j = 0; j < m; ++j) buf[j] = make(base + j);
+            f.write(reinterpret_cast<const char *>(buf), (std::streamsize) (sizeof(T) * m));
+        }
+    };
+    interleaved(px, py, pz);
+    generated(std::int32_t(0), [](std::uint64_t j) { return (std::int32_t) j; });
+    interleaved(vx, vy, vz);
+    blockHeader(8 * n);
+    f.write(reinterpret_cast<const char *>(an.data()), (std::streamsize) (8 * n));
+    blockHeader(8 * n);
+    f.write(reinterpret_cast<const char *>(d.mass.data()), (std::streamsize) (8 * n));
+    generated(std::int32_t(0), [&](std::uint64_t j) {
+        return (std::int32_t) (j < d.body_classes.size() ? orbitClassId(d.body_classes[j]) : 0);
+    });
+    generated(std::int64_t(0), [](std::uint64_t j) { return (std::int64_t) (j + 1); });
+    generated(std::int64_t(0), [](std::uint64_t j) { return (std::int64_t) j; });
+    f << '\n' << "</AppendedData>" << '\n' << "</VTKFile>" << '\n';
 }
 
 void nBodyAlgorithm::enableStreaming(const SimulationData &d) { streamData = &d; }

@@ -45,6 +45,18 @@ public:
     // byte-identical to the ones generateParaViewOutput writes.
     void enableStreaming(const SimulationData &simulationData);
 
+    // Binary snapshots (new, `--vtp_format=binary`): the same arrays as the ASCII .vtp, written as VTK
+    // XML "appended raw" blocks at full fp64 precision; the ASCII writer stays the byte-compatible default.
+    void setBinaryOutput(bool on) { binaryOutput = on; }
+
+    // Checkpoints (new, `--checkpoint=<path>` [`--checkpoint_every_vs=true`]): masses, positions and the
+    // integrator's velocities as a binary state file (host/StateFile.hpp) after the last step and, optionally, after
+    // every visualised step.  `--file=<checkpoint>` resumes; the continued trajectory is bit-identical.
+    void setCheckpoint(const std::string &path, bool everyVisualizedStep) {
+        checkpointPath = path;
+        checkpointEveryVisualizedStep = everyVisualizedStep;
+    }
+
     // energies of the current device state, stored under currentStep (reference nBodyAlgorithm.cpp:11-86)
     void computeEnergy(d_type::int_t currentStep);
     // |a| of the current device accelerations (reference nBodyAlgorithm.cpp:88-102)
@@ -59,6 +71,13 @@ private:
     const SimulationData *streamData = nullptr;      // non-null in streaming mode
     d_type::int_t stepsStreamed = 0;                  // .vtp files already written
     std::vector<double> lastPos_x, lastPos_y, lastPos_z;
+    bool binaryOutput = false;
+    std::string checkpointPath;
+    bool checkpointEveryVisualizedStep = false;
+    void writeStepFileBinary(d_type::int_t step, const SimulationData &simulationData);
+    // state = positions/velocities given (a visualised step's host copies) or, when null, read back from the device
+    void writeCheckpoint(const SimulationData &simulationData, double time, const std::vector<double> *pos[3],
+                         const std::vector<double> *vel[3]);
     void prepareOutputDirectory();
     void writeStepFile(d_type::int_t step, const SimulationData &simulationData);
     void streamStep(d_type::int_t step);

@@ -180,3 +180,98 @@ def test_vtp_and_pvd_are_byte_compatible(nb, oracle, tmp_path, golden_dir, strea
                 assert gv.shape == wv.shape and np.all(np.abs(gv - wv) <= 1.01e-5 * np.abs(wv) + 1e-300)
     last = open(os.path.join(d, "lastState.csv")).read().splitlines()
     assert last[0] == "position_x, position_y, position_z " and len(last) == 179
+
+
+# ---- binary state input, checkpoint / resume, binary snapshots ------------------------------------------
+def parse_appended_vtp(path):
+    """Minimal reader of the VTK XML 'appended raw' layout written by --vtp_format=binary."""
+    import re
+    raw = open(path, "rb").read()
+    marker = raw.index(b'<AppendedData encoding="raw">')
+    start = raw.index(b"_", marker) + 1
+    header = raw[:marker].decode()
+    dtypes = {"Float64": "<f8", "Int32": "<i4", "Int64": "<i8"}
+    arrays = {}
+    for m in re.finditer(r'<DataArray type="(\w+)" Name="([\w ]+)"(?: NumberOfComponents="(\d)")? format="appended" offset="(\d+)"/>', header):
+        typ, name, comps, off = m.group(1), m.group(2), int(m.group(3) or 1), int(m.group(4))
+        nbytes = int.from_bytes(raw[start + off:start + off + 8], "little")
+        a = np.frombuffer(raw[start + off + 8:start + off + 8 + nbytes], dtype=dtypes[typ])
+        arrays[name] = a.reshape(-1, comps) if comps > 1 else a
+    fields = {m.group(1): float(m.group(2)) for m in
+              re.finditer(r'Name="([\w ]+)" NumberOfTuples="1" format="ascii">\n(\S+)\n', header)}
+    assert raw.rstrip().endswith(b"</VTKFile>")
+    return header, arrays, fields
+
+
+@pytest.mark.parametrize("algorithm", ["naive", "BarnesHut"])
+def test_checkpoint_resume_is_bit_identical(nb, tmp_path, golden_dir, algorithm):
+    """10 steps in one run == 5 steps + checkpoint + 5 steps from the checkpoint, to the last bit of x and v."""
+    fixture = os.path.join(golden_dir, "solar_178.csv")
+    common = ["--dt=6h", "--vs=1d", "--algorithm=" + algorithm]
+    full = tmp_path / "full.nbstate"
+    run_exe(tmp_path / "a", fixture, "--t_end=60h", "--checkpoint=" + str(full), *common)
+    half = tmp_path / "half.nbstate"
+    run_exe(tmp_path / "b", fixture, "--t_end=30h", "--checkpoint=" + str(half), *common)
+    resumed = tmp_path / "resumed.nbstate"
+    run_exe(tmp_path / "c", str(half), "--t_end=30h", "--checkpoint=" + str(resumed), *common)
+    a, b, c = (nb.generators.read_state(p) for p in (full, half, resumed))
+    assert a["time"] == 2.5 and b["time"] == 1.25 and c["time"] == 2.5
+    assert c["names"] == a["names"] and a["names"][2] == "Earth"
+    for k in ("m", "x", "y", "z", "vx", "vy", "vz"):
+        assert np.array_equal(a[k], c[k]), k
+    assert not np.array_equal(a["x"], b["x"])
+
+
+def test_checkpoint_at_every_visualised_step(nb, tmp_path, golden_dir):
+    fixture = os.path.join(golden_dir, "solar_178.csv")
+    ck = tmp_path / "ck.nbstate"
+    d, _ = run_exe(tmp_path, fixture, "--dt=6h", "--t_end=2d", "--vs=1d", "--algorithm=naive", "--stream_output=true",
+                   "--checkpoint=" + str(ck), "--checkpoint_every_vs=true")
+    s = nb.generators.read_state(ck)
+    assert s["time"] == 2.0
+    last = read_last_state(d)
+    assert np.all(np.abs(last[:, 0] - s["x"]) <= 1.01e-5 * np.abs(s["x"]) + 1e-12)
+
+
+def test_binary_snapshots_hold_the_same_data_at_full_precision(nb, oracle, tmp_path, golden_dir):
+    fixture = os.path.join(golden_dir, "solar_178.csv")
+    names, classes, m, x, y, z, vx, vy, vz = load_csv(fixture)
+    flags = ["--dt=6h", "--t_end=2d", "--vs=1d", "--algorithm=BarnesHut", "--theta=0.5", "--energy=true"]
+    d, _ = run_exe(tmp_path, fixture, "--vtp_format=binary", *flags)
+    ref = oracle.simulate("BarnesHut", m, x, y, z, vx, vy, vz, 0.25, 2.0, 1.0, theta=0.5, energy=True)
+    for step in range(3):
+        header, arr, fields = parse_appended_vtp(os.path.join(d, "simulation_step%d.vtp" % step))
+        assert '<Piece NumberOfPoints="178" NumberOfVerts="178">' in header and 'Name="name"' not in header
+        want_pos = np.stack([ref["px"][step], ref["py"][step], ref["pz"][step]], axis=1)
+        want_vel = np.stack([ref["vx"][step], ref["vy"][step], ref["vz"][step]], axis=1)
+        scale = np.abs(want_pos).max()
+        assert arr["position"].shape == (178, 3) and np.all(np.abs(arr["position"] - want_pos) <= 1e-11 * scale)
+        assert np.all(np.abs(arr["velocity"] - want_vel) <= 1e-11 * np.abs(want_vel).max())
+        assert np.allclose(arr["acceleration"], ref["anorm"][step], rtol=1e-9, atol=0)
+        assert np.array_equal(arr["mass"], m)
+        assert np.array_equal(arr["body_id"], np.arange(178)) and np.array_equal(arr["connectivity"], np.arange(178))
+        assert np.array_equal(arr["offsets"], np.arange(1, 179))
+        assert arr["orbit_class"][0] == 15 and arr["orbit_class"][2] == 17
+        assert fields["kinetic energy"] == pytest.approx(ref["energy"][step][0], rel=1e-12)
+        assert fields["potential energy"] == pytest.approx(ref["energy"][step][1], rel=1e-12)
+    if True:   # step 0 is host arithmetic only: positions exactly as read
+        _, arr0, _ = parse_appended_vtp(os.path.join(d, "simulation_step0.vtp"))
+        assert np.array_equal(arr0["position"], np.stack([x, y, z], axis=1))
+
+
+def test_nameless_state_input_runs_and_writes_complete_arrays(nb, oracle, tmp_path):
+    """Synthetic bodies enter through the binary state file (no names / classes) instead of a CSV."""
+    n = 3000
+    m, x, y, z, vx, vy, vz = nb.generators.plummer(n, seed=2)
+    state = tmp_path / "plummer.nbstate"
+    nb.generators.write_state(state, m, x, y, z, vx, vy, vz)
+    d, _ = run_exe(tmp_path, str(state), "--dt=1h", "--t_end=3h", "--vs=1h", "--algorithm=BarnesHut", "--theta=0.5")
+    ref = oracle.simulate("BarnesHut", m, x, y, z, vx, vy, vz, 1.0 / 24, 3.0 / 24, 1.0 / 24, theta=0.5)
+    last = read_last_state(d)
+    want = ref["px"][ref["n_snap"] - 1]
+    assert np.all(np.abs(last[:, 0] - want) <= 1.01e-5 * np.abs(want) + 1e-12)
+    vtp = open(os.path.join(d, "simulation_step1.vtp")).read()
+    name_block = vtp.split('Name="name"')[1].split("</DataArray>")[0].split("\n")[1:-1]
+    class_block = vtp.split('Name="orbit_class"')[1].split("</DataArray>")[0].split("\n")[1:-1]
+    assert len(name_block) == n and set(name_block) == {" 0"}
+    assert len(class_block) == n and set(class_block) == {"0"}

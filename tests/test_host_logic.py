@@ -17,7 +17,7 @@ HOST = os.path.join(ROOT, "n-body-simulation_b200", "host")
 def shim():
     so = os.path.join(ROOT, "tests", "_host_shim.so")
     srcs = [os.path.join(ROOT, "tests", "host_shim.cpp")] + [os.path.join(HOST, f) for f in
-                                                             ("InputParser.cpp", "TimeConverter.cpp")]
+                                                             ("InputParser.cpp", "StateFile.cpp", "TimeConverter.cpp")]
     cxx = "/usr/bin/g++" if os.path.exists("/usr/bin/g++") else "g++"
     # Configuration.cpp needs nb_config_default from the CUDA library; the shim only needs initializeConfigValues,
     # so compile Configuration.cpp against the built library
@@ -28,6 +28,9 @@ def shim():
     L = C.CDLL(so)
     L.shim_convert_time.argtypes = [C.c_char_p, C.POINTER(C.c_double)]
     L.shim_split.argtypes = [C.c_char_p, C.c_char_p, C.c_int]
+    L.shim_convert_to_state.argtypes = [C.c_char_p, C.c_char_p, C.c_double]
+    L.shim_start_time.argtypes = [C.c_char_p]
+    L.shim_start_time.restype = C.c_double
     return L
 
 
@@ -84,6 +87,60 @@ def test_parse_solar_fixture(nb, shim, golden_dir):
     assert tags[0] == "Sun|STA" and arrs[0][0] == 1.98847e30
     assert tags[2] == "Earth|PLA" and arrs[0][2] == pytest.approx(5.97219e24)
     assert np.hypot(arrs[1][2], arrs[2][2]) == pytest.approx(0.9833, abs=2e-3)  # Earth near perihelion on 1 Jan 2000
+
+
+def _parse(shim, path, n):
+    arrs = [np.zeros(n) for _ in range(7)]
+    names = C.create_string_buffer(1 << 16)
+    shim.shim_parse_csv.argtypes = [C.c_char_p, C.c_int] + [C.POINTER(C.c_double)] * 7 + [C.c_char_p, C.c_int]
+    got = shim.shim_parse_csv(str(path).encode(), n, *[a.ctypes.data_as(C.POINTER(C.c_double)) for a in arrs], names, 1 << 16)
+    return got, arrs, names.value.decode()
+
+
+def test_state_file_round_trip_keeps_every_bit(nb, shim, golden_dir, tmp_path):
+    """CSV -> binary state (C++ writer) -> C++ reader and Python reader: all seven arrays bitwise, names kept."""
+    csv = os.path.join(golden_dir, "solar_178.csv")
+    state = tmp_path / "solar.nbstate"
+    assert shim.shim_convert_to_state(csv.encode(), str(state).encode(), 12.5) == 178
+    n0, a0, tags0 = _parse(shim, csv, 178)
+    n1, a1, tags1 = _parse(shim, state, 178)
+    assert n0 == n1 == 178 and tags0 == tags1
+    for u, v in zip(a0, a1):
+        assert np.array_equal(u, v)
+    assert shim.shim_start_time(str(state).encode()) == 12.5 and shim.shim_start_time(csv.encode()) == 0.0
+    py = nb.generators.read_state(state)
+    assert py["time"] == 12.5 and py["names"][2] == "Earth" and py["classes"][0] == "STA"
+    for u, k in zip(a0, ("m", "x", "y", "z", "vx", "vy", "vz")):
+        assert np.array_equal(u, py[k])
+
+
+def test_state_file_written_by_python_is_read_by_the_host(nb, shim, tmp_path):
+    m, x, y, z, vx, vy, vz = nb.generators.plummer(1000, seed=4)
+    path = tmp_path / "p.nbstate"
+    nb.generators.write_state(path, m, x, y, z, vx, vy, vz, time=3.0)
+    n, arrs, tags = _parse(shim, path, 1000)
+    assert n == 1000 and tags == ""            # no name table
+    for u, v in zip(arrs, (m, x, y, z, vx, vy, vz)):
+        assert np.array_equal(u, v)
+    assert shim.shim_start_time(str(path).encode()) == 3.0
+
+
+def test_state_file_errors(nb, shim, tmp_path):
+    m, x, y, z, vx, vy, vz = nb.generators.uniform_sphere(64, seed=1)
+    good = tmp_path / "g.nbstate"
+    nb.generators.write_state(good, m, x, y, z, vx, vy, vz)
+    raw = good.read_bytes()
+    cut = tmp_path / "cut.nbstate"
+    cut.write_bytes(raw[:-16])                  # truncated array
+    assert _parse(shim, cut, 64)[0] == -1
+    ver = tmp_path / "ver.nbstate"
+    ver.write_bytes(raw[:8] + (2).to_bytes(4, "little") + raw[12:])   # unknown version
+    assert _parse(shim, ver, 64)[0] == -1
+    empty = tmp_path / "empty.nbstate"
+    nb.generators.write_state(empty, *[np.zeros(0)] * 7)
+    assert _parse(shim, empty, 1)[0] == 0       # valid, no bodies (main() rejects it like an empty CSV)
+    with pytest.raises(ValueError):
+        nb.generators.write_state(tmp_path / "bad", m, x[:5], y, z, vx, vy, vz)
 
 
 def test_config_values_match_oracle(nb, shim, oracle):
