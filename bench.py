@@ -12,7 +12,8 @@ interactions, self term included as in the reference), closing kick.  metric = b
     the timed region).  `roofline` is the FP64 pipe: achieved = 21 flop x N^2 / kernel time (CUDA events on the
     launching stream), peak = a DFMA-chain microbenchmark run in the same process (MEASURED_PEAKS.json has no fp64
     figure).  `bh` adds the secondary metric (Barnes-Hut steps/s, uniform sphere, theta = 0.5) with its HBM roofline.
-  * --impl reference: the CPU oracle port of the reference's loop (OpenMP, all host threads) on a bounded row sample.
+  * --impl reference: the reference's own NaiveAlgorithm::computeAccelerations_opt_N (unmodified source compiled with
+    g++/OpenMP into oracle/_ref) on all host threads, over a bounded sample of the workload.
 Multi-GPU: launched by torchrun with one rank per GPU; targets are sharded by contiguous ranges, accelerations are
 all-gathered by the library's NCCL communicator (strong scaling: total work fixed).
 """
@@ -128,68 +129,103 @@ def flush_l2(torch, dev):
 
 
 # ---------------------------------------------------------------------------------------------------------------------
+def host_cores():
+    """All host cores this process may use (torchrun exports OMP_NUM_THREADS=1, which would hide them)."""
+    try:
+        return len(os.sched_getaffinity(0))
+    except AttributeError:
+        return os.cpu_count() or 1
+
+
+class CpuReference:
+    """The reference's own CPU implementation of the naive path, timed on the host cores.
+
+    kind "reference": oracle/_ref/libnbody_ref.so, the reference's unmodified NaiveAlgorithm::computeAccelerations_opt_N
+    compiled with g++/OpenMP (oracle/Makefile).  kind "port": the oracle restatement, only if oracle/_ref is missing.
+    The reference evaluates all N^2 pairs of the bodies it is given, so the bounded sample is the first n_s bodies of
+    the workload's N = 2^20 Plummer set (the CPU rate in interactions/s does not depend on N)."""
+
+    def __init__(self, nb, n):
+        sys.path.insert(0, os.path.join(ROOT, "oracle"))
+        self.m, self.x, self.y, self.z, *_ = nb.generators.plummer(n, seed=1)
+        self.n = n
+        self.cores = host_cores()
+        try:
+            import refimpl as R
+            if not R.available():
+                raise RuntimeError("oracle/_ref not built")
+            R.lib()
+            R.set_threads(self.cores)
+            self.R, self.kind = R, "reference"
+        except Exception as e:  # noqa: BLE001 - fall back to the restatement, and say so
+            import oracle as O
+            self.O, self.kind, self.why = O, "port", repr(e)
+        self.stage = 0
+
+    def evaluate(self, ns, stage=None):
+        m, x, y, z = (a[:ns] for a in (self.m, self.x, self.y, self.z))
+        t0 = time.perf_counter()
+        if self.kind == "reference":
+            self.R.naive_accel(m, x, y, z, opt_stage=self.stage if stage is None else stage, block_size=64)
+        else:
+            self.O.naive_accel(m, x, y, z, nthreads=self.cores)
+        return time.perf_counter() - t0
+
+    def calibrate(self, seconds):
+        """Pick the faster of the reference's opt stages 0 and 2 and a sample size worth ~`seconds` of CPU work."""
+        probe = min(self.n, 16384)
+        t = {0: self.evaluate(probe, 0)}
+        if self.kind == "reference":
+            t[2] = self.evaluate(probe, 2)
+        self.stage = min(t, key=t.get)
+        rate = probe * float(probe) / max(t[self.stage], 1e-6)
+        ns = probe
+        while ns * 2 <= self.n and (2.0 * ns) ** 2 / rate <= seconds:
+            ns *= 2
+        return ns
+
+    def describe(self, ns, dt=None):
+        what = ("reference NaiveAlgorithm::computeAccelerations_opt_%d (unmodified source, g++ -O3 -fopenmp via oracle/_ref)"
+                % self.stage) if self.kind == "reference" else "oracle restatement of the reference loop (oracle/_ref missing)"
+        s = "first %d bodies of the N=%d Plummer set, all %.3g pairs, %s" % (ns, self.n, ns * float(ns), what)
+        return s + (", %.1f s" % dt if dt is not None else "")
+
+
 def run_reference(args, rank, world):
-    """The reference's CPU implementation of the path, restated (oracle port), timed on the host cores."""
+    """--impl reference: the reference's CPU implementation of the path on the host cores (rank 0 only)."""
     if rank != 0:
         return
-    sys.path.insert(0, os.path.join(ROOT, "oracle"))
-    import oracle as O
     nb = importlib.import_module("n-body-simulation_b200")
     n = args.n
-    m, x, y, z, vx, vy, vz = nb.generators.plummer(n, seed=1)
-    threads = host_threads(O)
-    # bounded sample: R target rows against all N sources, sized for ~5 s per step from a short probe
-    t0 = time.perf_counter()
-    O.naive_accel(m, x, y, z, rows=(0, 64), nthreads=threads)
-    probe = time.perf_counter() - t0
-    rate = 64.0 * n / max(probe, 1e-6)
-    rows = int(min(n, max(64, (rate * 5.0) // n)))
-    rows -= rows % 8
-    for _ in range(args.warmup if args.warmup < 2 else 1):
-        O.naive_accel(m, x, y, z, rows=(0, rows), nthreads=threads)
+    cpu = CpuReference(nb, n)
+    ns = cpu.calibrate(seconds=6.0)
+    for _ in range(min(args.warmup, 1)):
+        cpu.evaluate(ns)
     t0 = time.perf_counter()
     for _ in range(args.steps):
-        O.naive_accel(m, x, y, z, rows=(0, rows), nthreads=threads)
+        cpu.evaluate(ns)
     dt = time.perf_counter() - t0
-    value = rows * float(n) * args.steps / dt
-    sample = "rows [0,%d) of N=%d against all N sources (%.3g interactions per step)" % (rows, n, rows * float(n))
+    value = ns * float(ns) * args.steps / dt
     line = {
         "impl": "reference", "metric": "body-interactions/s", "value": value, "unit": "interactions/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3,
         "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": {"workload": "naive all-pairs fp64, Plummer sphere N=%d (BASELINE configs[1])" % n,
-                   "note": "reference SYCL toolchain absent: CPU oracle port (OpenMP, -ffp-contract=off), bounded sample"},
-        "cpu_baseline": {"value": value, "unit": "interactions/s", "cores": threads, "kind": "port", "sample": sample},
+                   "note": "CPU arm: each step is one all-pairs evaluation over a bounded sample of the workload"},
+        "cpu_baseline": {"value": value, "unit": "interactions/s", "cores": cpu.cores, "kind": cpu.kind,
+                         "sample": cpu.describe(ns)},
         "e2e": {"value": value, "unit": "interactions/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
     emit(line)
 
 
-def host_threads(O):
-    """All host cores this process may use (torchrun exports OMP_NUM_THREADS=1, which would hide them)."""
-    try:
-        return max(O.max_threads(), len(os.sched_getaffinity(0)))
-    except AttributeError:
-        return max(O.max_threads(), os.cpu_count() or 1)
-
-
 def cpu_baseline(nb, n, seconds=12.0):
-    sys.path.insert(0, os.path.join(ROOT, "oracle"))
-    import oracle as O
-    m, x, y, z, *_ = nb.generators.plummer(n, seed=1)
-    threads = host_threads(O)
-    t0 = time.perf_counter()
-    O.naive_accel(m, x, y, z, rows=(0, 64), nthreads=threads)
-    probe = time.perf_counter() - t0
-    rate = 64.0 * n / max(probe, 1e-6)
-    rows = int(min(n, max(64, (rate * seconds) // n)))
-    rows -= rows % 8
-    t0 = time.perf_counter()
-    O.naive_accel(m, x, y, z, rows=(0, rows), nthreads=threads)
-    dt = time.perf_counter() - t0
-    return {"value": rows * float(n) / dt, "unit": "interactions/s", "cores": threads, "kind": "port",
-            "sample": "rows [0,%d) of N=%d against all N sources, %.1f s" % (rows, n, dt)}
+    cpu = CpuReference(nb, n)
+    ns = cpu.calibrate(seconds)
+    dt = cpu.evaluate(ns)
+    return {"value": ns * float(ns) / dt, "unit": "interactions/s", "cores": cpu.cores, "kind": cpu.kind,
+            "sample": cpu.describe(ns, dt)}
 
 
 # ---------------------------------------------------------------------------------------------------------------------

@@ -29,11 +29,16 @@ void BarnesHutAlgorithm::startSimulation(const SimulationData &simulationData) {
     openDevice(simulationData);
     // same sequence names as the reference's times.json (BarnesHutAlgorithm.cpp:79-100); the phases of the lock-based
     // builder map onto the sort-based one: "Sort bodies for subtrees" = keys + radix sort, "Build subtrees" = node
-    // emission.  "Build octree to level" / "Prepare subtrees" / "Sort bodies" have no counterpart and stay empty.
+    // emission.  "Build octree to level" / "Prepare subtrees" / "Sort bodies" have no counterpart (the in-order
+    // permutation falls out of the radix sort): they are recorded as 0 ms per step so that times.json carries the same
+    // keys and the same number of entries as the reference's file (ParallelOctreeTopDownSubtrees.cpp:76-92).
     for (const char *name : {"Total Time", "Octree creation", "Acceleration Kernel Time", "AABB creation",
-                             "Compute center of mass", "Sort bodies for subtrees", "Build subtrees"})
+                             "Compute center of mass", "Build octree to level", "Prepare subtrees",
+                             "Sort bodies for subtrees", "Build subtrees"})
         timer.addTimingSequence(name);
-    runTimeLoop(simulationData, [this]() {
+    const bool sorted = configuration::barnes_hut_algorithm::sortBodies;
+    if (sorted) timer.addTimingSequence("Sort bodies");
+    runTimeLoop(simulationData, [this, sorted]() {
         octree.buildOctree(timer);
         computeAccelerations();
         double ms[NB_T_COUNT];
@@ -45,5 +50,8 @@ void BarnesHutAlgorithm::startSimulation(const SimulationData &simulationData) {
         timer.addTimeToSequence("Sort bodies for subtrees", ms[NB_T_KEYS_SORT]);
         timer.addTimeToSequence("Build subtrees", ms[NB_T_BUILD]);
         timer.addTimeToSequence("Compute center of mass", ms[NB_T_COM]);
+        timer.addTimeToSequence("Build octree to level", 0.0);
+        timer.addTimeToSequence("Prepare subtrees", 0.0);
+        if (sorted) timer.addTimeToSequence("Sort bodies", 0.0);
     });
 }

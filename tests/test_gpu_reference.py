@@ -1,0 +1,276 @@
+"""The CUDA path (through the C ABI and through the reference-facing executable) against the reference ITSELF:
+  * tests/golden/reference_vectors.npz -- outputs of the reference committed as fixtures (tools/make_golden.py);
+  * oracle/_ref -- the reference's unmodified sources built with g++ (oracle/Makefile), run side by side here.
+Tolerances: fp64 accelerations 1e-10 relative (BASELINE.json north_star); tree structure, per-node mass and
+mass-weighted sums, in-order permutation, leapfrog updates: bit exact; output files: byte for byte except where a
+value sits within 1e-10 relative of a 6-significant-digit rounding boundary."""
+import glob
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+EXE = os.path.join(ROOT, "n-body-simulation_b200", "N_Body_Simulation")
+TOL = 1e-10
+CANON_KEYS = ("depth", "path_hi", "path_lo", "kind", "body", "count", "edge", "minx", "miny", "minz", "mass", "comx",
+              "comy", "comz")
+
+
+def relerr(a, b):
+    a = np.stack(a, 1); b = np.stack(b, 1)
+    return float((np.linalg.norm(a - b, axis=1) / np.maximum(np.linalg.norm(b, axis=1), 1e-300)).max())
+
+
+@pytest.fixture(scope="module")
+def ref():
+    import refimpl as R
+    if not R.available():
+        pytest.skip("oracle/_ref is not built and /root/reference is absent")
+    R.lib()
+    return R
+
+
+@pytest.fixture(scope="module")
+def golden(golden_dir):
+    return np.load(os.path.join(golden_dir, "reference_vectors.npz"))
+
+
+def inputs(golden, tag):
+    return [golden["%s_in_%s" % (tag, k)] for k in ("m", "x", "y", "z", "vx", "vy", "vz")]
+
+
+# ---- committed outputs of the reference ---------------------------------------------------------------------------------------
+@pytest.mark.parametrize("tag", ["plummer", "uniform"])
+def test_naive_and_energy_against_reference_vectors(nb, golden, tag):
+    m, x, y, z, vx, vy, vz = inputs(golden, tag)
+    for stage in (0, 1, 2):
+        c = nb.Context(device=0, opt_stage=stage, block_size=64)
+        c.set_bodies(m, x, y, z, vx, vy, vz)
+        c.naive_accel()
+        assert relerr(c.accelerations(), golden["%s_naive_opt%d" % (tag, stage)]) <= TOL
+        e = np.array(c.energy())
+        assert np.allclose(e, golden["%s_energy" % tag], rtol=1e-12, atol=0)
+        c.close()
+
+
+@pytest.mark.parametrize("tag", ["plummer", "uniform"])
+def test_tree_against_reference_vectors(nb, golden, tag):
+    """Same octree node set as BOTH reference builders, bitwise cell geometry, mass and mass-weighted sums."""
+    m, x, y, z, *_ = inputs(golden, tag)
+    c = nb.Context(device=0)
+    c.set_bodies(m, x, y, z)
+    c.bh_build()
+    got = c.bh_export_canonical()
+    for builder in ("subtrees", "synchronized"):
+        for k in CANON_KEYS:
+            assert np.array_equal(got[k], golden["%s_tree_%s_%s" % (tag, builder, k)]), (builder, k)
+        assert np.array_equal(c.bh_aabb(), golden["%s_tree_%s_aabb" % (tag, builder)])
+        assert np.array_equal(c.bh_sorted_bodies(), golden["%s_tree_%s_sorted" % (tag, builder)])
+    c.close()
+
+
+@pytest.mark.parametrize("tag", ["plummer", "uniform"])
+@pytest.mark.parametrize("theta", [0.2, 0.5, 1.05])
+def test_barnes_hut_against_reference_vectors(nb, golden, tag, theta):
+    m, x, y, z, *_ = inputs(golden, tag)
+    c = nb.Context(device=0, theta=theta)
+    c.set_bodies(m, x, y, z)
+    c.bh_build()
+    c.bh_accel()
+    assert relerr(c.accelerations(), golden["%s_bh_theta%g" % (tag, theta)]) <= TOL
+    c.close()
+
+
+def test_three_body_case_of_the_reference_tests(nb, golden):
+    c = nb.Context(device=0)
+    c.set_bodies([10.0, 10.0, 10.0], [0.0, 0.0, 2.0], [1.0, 0.0, 0.0], [0.0, 2.0, 0.0])
+    c.bh_build()
+    assert np.array_equal(c.bh_aabb(), golden["three_aabb"])
+    assert list(c.bh_sorted_bodies()) == list(golden["three_sorted"])
+    can = c.bh_export_canonical()
+    assert can["mass"][0] == golden["three_sum_masses"][0] == 30.0
+    c.close()
+
+
+def gpu_simulate(nb, algorithm, m, x, y, z, vx, vy, vz, dt, t_end, vs, theta):
+    """The reference's time loop (NaiveAlgorithm.cpp:82-259 / BarnesHutAlgorithm.cpp:102-276) through the C ABI."""
+    c = nb.Context(device=0, theta=theta)
+    c.set_bodies(m, x, y, z, vx, vy, vz)
+
+    def forces():
+        if algorithm == "naive":
+            c.naive_accel()
+        else:
+            c.bh_build(); c.bh_accel()
+
+    s = {k: [] for k in ("px", "py", "pz", "vx", "vy", "vz", "anorm", "energy")}
+    forces()
+    s["px"].append(x.copy()); s["py"].append(y.copy()); s["pz"].append(z.copy())
+    s["energy"].append(c.energy())
+    s["anorm"].append(c.acceleration_norms())
+    time, since = dt, dt
+    while time <= t_end + 0.000001:
+        vis = abs(since - vs) < 0.000001
+        c.leapfrog_part1(dt)
+        if vis:
+            p = c.positions()
+            s["px"].append(p[0]); s["py"].append(p[1]); s["pz"].append(p[2])
+        forces()
+        c.leapfrog_part2(dt)
+        if vis:
+            s["anorm"].append(c.acceleration_norms())
+            v = c.velocities()
+            s["vx"].append(v[0]); s["vy"].append(v[1]); s["vz"].append(v[2])
+            s["energy"].append(c.energy())
+            since = 0.0
+        time += dt
+        since += dt
+    c.close()
+    return s
+
+
+@pytest.mark.parametrize("tag", ["plummer", "uniform"])
+@pytest.mark.parametrize("algorithm,theta", [("naive", 1.05), ("BarnesHut", 0.5)])
+def test_trajectories_against_reference_vectors(nb, golden, tag, algorithm, theta):
+    """24 leapfrog steps: positions within 1e-9 of the system radius, |a| and energies to 1e-9 relative."""
+    m, x, y, z, vx, vy, vz = inputs(golden, tag)
+    s = gpu_simulate(nb, algorithm, m, x, y, z, vx, vy, vz, 1.0 / 24, 1.0, 0.25, theta)
+    key = "%s_sim_%s_" % (tag, algorithm)
+    want_p = golden[key + "px"]
+    assert len(s["px"]) == want_p.shape[0] == 5
+    radius = float(np.abs(np.stack([x, y, z])).max())
+    for k in ("px", "py", "pz"):
+        assert np.abs(np.array(s[k]) - golden[key + k]).max() <= 1e-9 * radius
+    # snapshot 0 of the velocity maps holds the ADJUSTED input velocities (output only); 1.. the integrator's
+    for k in ("vx", "vy", "vz"):
+        want = golden[key + k][1:]
+        assert np.abs(np.array(s[k]) - want).max() <= 1e-9 * np.abs(want).max()
+    assert np.allclose(np.array(s["anorm"]), golden[key + "anorm"], rtol=1e-8, atol=0)
+    assert np.allclose(np.array(s["energy"]), golden[key + "energy"], rtol=1e-9, atol=0)
+
+
+# ---- side by side with the reference build ------------------------------------------------------------------------------------
+@pytest.mark.parametrize("n,gen,seed", [(3, "plummer", 1), (1000, "uniform_sphere", 2), (8192, "plummer", 3)])
+def test_naive_side_by_side(nb, ref, n, gen, seed):
+    m, x, y, z, *_ = getattr(nb.generators, gen)(n, seed=seed)
+    c = nb.Context(device=0)
+    c.set_bodies(m, x, y, z)
+    c.naive_accel()
+    assert relerr(c.accelerations(), ref.naive_accel(m, x, y, z, opt_stage=2)) <= TOL
+    c.close()
+
+
+@pytest.mark.parametrize("builder", ["subtrees", "synchronized"])
+@pytest.mark.parametrize("n,gen,seed", [(2, "plummer", 1), (777, "uniform_sphere", 2), (20000, "plummer", 3),
+                                        (60000, "uniform_sphere", 4)])
+def test_tree_side_by_side(nb, ref, builder, n, gen, seed):
+    m, x, y, z, *_ = getattr(nb.generators, gen)(n, seed=seed)
+    m = m * (1.0 + 0.5 * np.cos(np.arange(n)))
+    c = nb.Context(device=0)
+    c.set_bodies(m, x, y, z)
+    c.bh_build()
+    t = ref.Tree(m, x, y, z, builder=builder)
+    assert c.bh_tree_info().num_nodes_canonical == t.num_nodes
+    assert np.array_equal(c.bh_aabb(), t.aabb())
+    got, want = c.bh_export_canonical(), t.canonical()
+    for k in CANON_KEYS:
+        assert np.array_equal(got[k], want[k]), k
+    assert np.array_equal(c.bh_sorted_bodies(), t.sorted_bodies)
+    c.close()
+
+
+@pytest.mark.parametrize("theta", [0.3, 0.5, 1.05])
+@pytest.mark.parametrize("n,gen,seed", [(500, "plummer", 1), (30000, "uniform_sphere", 2)])
+def test_barnes_hut_side_by_side(nb, ref, n, gen, seed, theta):
+    m, x, y, z, *_ = getattr(nb.generators, gen)(n, seed=seed)
+    c = nb.Context(device=0, theta=theta)
+    c.set_bodies(m, x, y, z)
+    c.bh_build()
+    c.bh_accel()
+    ax, ay, az, nodes = ref.bh_accel(m, x, y, z, theta)
+    assert c.bh_tree_info().num_nodes_canonical == nodes
+    assert relerr(c.accelerations(), (ax, ay, az)) <= TOL
+    c.close()
+
+
+# ---- executables: ours and the reference's on the same command line -----------------------------------------------------------
+def run_both(ref, tmp_path, fixture, flags):
+    outs = []
+    for name, exe in (("ours", EXE), ("reference", ref.EXE_PATH)):
+        out = tmp_path / name
+        r = subprocess.run([exe, "--file=" + fixture, "--vs_dir=" + str(out)] + flags, capture_output=True, text=True,
+                           timeout=900)
+        assert r.returncode == 0, (name, r.stderr[-2000:])
+        dirs = glob.glob(str(out / "*"))
+        assert len(dirs) == 1
+        outs.append((dirs[0], r.stdout))
+    return outs
+
+
+def close_tokens(a, b):
+    """Two printed numbers that differ only because the values straddle a rounding boundary of the 6-digit print."""
+    try:
+        fa, fb = float(a), float(b)
+    except ValueError:
+        return False
+    return abs(fa - fb) <= 1.001e-5 * max(abs(fa), abs(fb)) + 1e-300
+
+
+def assert_same_text(path_a, path_b, max_boundary_tokens):
+    la, lb = open(path_a).read().splitlines(), open(path_b).read().splitlines()
+    assert len(la) == len(lb), (path_a, len(la), len(lb))
+    boundary = 0
+    for i, (a, b) in enumerate(zip(la, lb)):
+        if a == b:
+            continue
+        ta, tb = a.replace(",", " ").split(), b.replace(",", " ").split()
+        assert len(ta) == len(tb), (path_a, i, a, b)
+        for u, v in zip(ta, tb):
+            if u != v:
+                assert close_tokens(u, v), (path_a, i, u, v)
+                boundary += 1
+    assert boundary <= max_boundary_tokens, (path_a, boundary)
+    return boundary
+
+
+@pytest.mark.parametrize("algorithm,extra", [("naive", ["--opt_stage=2", "--block_size=64"]),
+                                             ("BarnesHut", ["--theta=0.5"]),
+                                             ("BarnesHut", ["--sort_bodies=false", "--wg_size_barnes_hut=32"])])
+def test_output_files_equal_the_reference_executable(nb, ref, tmp_path, golden_dir, algorithm, extra):
+    """Same flags, same CSV: simulation.pvd, every simulation_step<i>.vtp and lastState.csv equal the reference's files
+    (ASCII, 6 significant digits).  A handful of tokens may differ in the last printed digit when a value sits on a
+    rounding boundary (the accelerations agree to ~1e-15, not bitwise)."""
+    fixture = os.path.join(golden_dir, "solar_178.csv")
+    flags = ["--dt=1h", "--t_end=20d", "--vs=2d", "--algorithm=" + algorithm, "--energy=true"] + extra
+    (ours, out_o), (theirs, out_r) = run_both(ref, tmp_path, fixture, flags)
+    names_o = sorted(f for f in os.listdir(ours) if f != "times.json")
+    names_r = sorted(f for f in os.listdir(theirs) if f != "times.json")
+    assert names_o == names_r and len(names_o) == 2 + 11
+    total = 0
+    for f in names_o:
+        total += assert_same_text(os.path.join(ours, f), os.path.join(theirs, f), max_boundary_tokens=8)
+    assert total <= 20
+    # the per-step console lines of the time loop are the same
+    assert [l for l in out_o.splitlines() if l.startswith("Finished")] == \
+           [l for l in out_r.splitlines() if l.startswith("Finished")]
+
+
+def test_times_json_has_the_reference_keys(nb, ref, tmp_path, golden_dir):
+    import json
+    fixture = os.path.join(golden_dir, "solar_178.csv")
+    for algorithm in ("naive", "BarnesHut"):
+        (ours, _), (theirs, _) = run_both(ref, tmp_path / algorithm, fixture,
+                                          ["--dt=1h", "--t_end=2d", "--vs=1d", "--algorithm=" + algorithm])
+        a = json.load(open(os.path.join(ours, "times.json")))
+        b = json.load(open(os.path.join(theirs, "times.json")))
+        missing = set(b) - set(a)
+        assert not missing, missing
+        for k, v in b.items():
+            if isinstance(v, list):
+                assert len(a[k]) == len(v), k         # one entry per step, as in the reference
+            elif k != "device":
+                assert a[k] == v, k
