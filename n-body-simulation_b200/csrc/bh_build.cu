@@ -479,7 +479,7 @@ int nbk_bh_reserve(nb_ctx *ctx) {
     NB_CHECK(nb_alloc(ctx, &b.hist, scratch));
     NB_CHECK(nb_alloc(ctx, &b.aabb_dev, 8));
     NB_CHECK(nb_alloc(ctx, &b.aabb_partial, 6 * 1024));
-    NB_CHECK(nb_alloc(ctx, &b.dev_flags, 8));
+    NB_CHECK(nb_alloc(ctx, &b.dev_flags, 8 + 1024));   // 8 flag words + per-SM tile counters of the traversal
     NB_CHECK(nb_alloc(ctx, &b.stat_totals, 8));
     NB_CUDA(ctx, cudaMemsetAsync(b.dev_flags, 0, 8 * sizeof(uint32_t), ctx->stream));
     b.cap_bodies = n;

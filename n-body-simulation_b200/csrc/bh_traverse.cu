@@ -18,6 +18,8 @@
 // Payload per visited node: 32 B {com xyz, mass} + 8 B {skip, leaf|body / depth} = 40 B.
 #include "common.cuh"
 
+#include <algorithm>
+
 #define NB_BH_MAX_LEVELS 64
 
 namespace {
@@ -153,6 +155,154 @@ bh_traverse_kernel(const double4 *__restrict__ com, const uint2 *__restrict__ me
             a += __shfl_xor_sync(0xffffffffu, a, o);
         }
         if (lane == 0) { atomicAdd(&totals[0], v); atomicAdd(&totals[1], a); }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// Production walk: acceptance test on the integer pipe, SM-local tile queues.
+//
+// Same traversal and the same interaction sets as bh_traverse_kernel above (kept as walk_variant 5 for A/B runs).
+//   * D = dx^2 + dy^2 + dz^2 + eps2 is ONE fma chain (eps2 folded into the first term) and serves both the acceptance
+//     test and the force;
+//   * positive doubles order like their bit patterns, so "D > (edge_d/theta)^2" is decided by comparing HIGH WORDS:
+//     W_d = hiword((edge_0/theta)^2) - (depth << 21)  (the edge halves exactly per level); accept when
+//     hiword(D) >= W_d + 2, open when hiword(D) <= W_d - 2.  The band in between (relative width 2^-19) and every
+//     depth for which eps2 is not negligible against (edge_d/theta)^2 take the oracle's exact expression
+//     (BarnesHutAlgorithm.cpp:355-359) with correctly rounded operations, so the decision is the reference's.  No
+//     per-depth fp64 thresholds, nothing spills under the 48-register budget (40 warps per SM);
+//   * PERSIST: the grid only fills the machine and every WARP draws 32-body tiles from a queue that belongs to the SM
+//     it runs on (the sorted body range is cut into one contiguous chunk per SM; a warp whose queue is empty steals
+//     from the following queues).  The ~40 warps resident on an SM therefore walk neighbouring bodies at the same time
+//     and share the node records they pull into that SM's L1 -- the hardware block scheduler would hand an SM blocks
+//     that are 148 blocks apart -- and no CTA is ever re-launched.  ncu at N = 2^24: L1 hit rate 65 % -> 73 %,
+//     warps active 57 % -> 62 %, 89.6 ms -> 85.1 ms.  tile_counters: one uint32 per queue, zeroed before the launch.
+// Explored on top of this and rejected (N = 2^24, theta = 0.5, all parity-green): issuing the next node's loads before
+// the force arithmetic (software pipelining: 95 ms, the 12 extra live registers cost 20 % of the resident warps);
+// prefetch.global.L1 of the next node (98-102 ms); ticketed one-tile-per-warp assignment (87 ms); interleaved runs of
+// tiles instead of contiguous chunks (no better than contiguous).
+// ---------------------------------------------------------------------------------------------------------------------
+template <bool STATS, bool PERSIST>
+__global__ void __launch_bounds__(256, 5)
+bh_traverse_iw_kernel(const double4 *__restrict__ com, const uint2 *__restrict__ meta, const uint32_t *__restrict__ flags,
+                      uint64_t n_bodies, const double *__restrict__ aabb, const double *__restrict__ sx,
+                      const double *__restrict__ sy, const double *__restrict__ sz, uint64_t s_begin, uint64_t s_end,
+                      double theta, double eps2, double G, double *__restrict__ asx, double *__restrict__ asy,
+                      double *__restrict__ asz, uint32_t *__restrict__ visits, unsigned long long *__restrict__ totals,
+                      uint32_t *__restrict__ tile_counters, uint32_t n_chunks) {
+    const double edge0 = aabb[6];
+    const double ratio0 = (edge0 / theta) * (edge0 / theta);
+    const bool scalable = ratio0 > 1e-200 && ratio0 < 1e200;   // theta == 0 or absurd boxes: always the exact branch
+    const int W0 = __double2hiint(ratio0);
+    // fast decisions need eps2 <= 2^-24 (edge_d/theta)^2 and a normal threshold: depth << 21 must stay below t_lim
+    int w_min = __double2hiint(eps2) + (24 << 20);
+    if (w_min < (64 << 20)) w_min = 64 << 20;
+    const uint32_t t_lim = (scalable && W0 > w_min) ? (uint32_t) (W0 - w_min) : 0u;
+    const uint32_t n_nodes = (uint32_t) n_bodies + flags[1];
+    // a failed build (depth / pool flag) leaves no valid tree: produce zeros instead of walking garbage
+    const bool tree_ok = flags[0] == 0;
+    const int lane = threadIdx.x & 31;
+    const uint64_t tiles_total = (s_end - s_begin + 31) >> 5;
+    const uint32_t T = PERSIST ? (uint32_t) ((tiles_total + n_chunks - 1) / n_chunks) : 0u;
+    uint32_t home = 0, probe = 0;
+    if (PERSIST) {
+        asm("mov.u32 %0, %%smid;" : "=r"(home));
+        home %= n_chunks;
+    }
+    uint64_t tile = ((uint64_t) blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    unsigned long long nvis_w = 0, nacc_w = 0;
+    for (;;) {
+        if constexpr (PERSIST) {
+            bool have = false;
+            while (probe < n_chunks) {
+                uint32_t cidx = home + probe;
+                if (cidx >= n_chunks) cidx -= n_chunks;
+                uint32_t t = 0;
+                if (lane == 0) t = atomicAdd(&tile_counters[cidx], 1u);
+                t = __shfl_sync(0xffffffffu, t, 0);
+                tile = (uint64_t) cidx * T + t;
+                if (t < T && tile < tiles_total) { have = true; break; }
+                ++probe;   // this queue is empty for good: own queue first, then steal from the following ones
+            }
+            if (!have) break;
+        } else {
+            if (tile >= tiles_total) break;
+        }
+        const uint64_t b = s_begin + tile * 32 + lane;
+        const bool valid = b < s_end;
+        const uint32_t me = (uint32_t) b;
+        double px = 0, py = 0, pz = 0;
+        if (valid) { px = sx[b]; py = sy[b]; pz = sz[b]; }
+        double ax = 0, ay = 0, az = 0;
+        uint32_t next = (valid && tree_ok) ? 0u : 0xffffffffu;
+        uint32_t nvis = 0, nacc = 0;
+
+        uint32_t cur = __reduce_min_sync(0xffffffffu, next);
+        while (cur < n_nodes) {
+            if (next == cur) {
+                const double4 c = com[cur];   // warp-uniform address: one broadcast transaction
+                const uint2 mt = meta[cur];
+                const double dx = c.x - px, dy = c.y - py, dz = c.z - pz;
+                const double D = fma(dz, dz, fma(dy, dy, fma(dx, dx, eps2)));
+                // SUM_MASSES == 0 nodes are invisible in the reference (BarnesHutAlgorithm.cpp:349): massless bodies,
+                // and cells that hold only massless bodies, are neither counted nor opened.  Their contribution is
+                // exactly 0.0 either way (the build stores a finite record for them), so only the instrumented build
+                // pays for the check that keeps the visit counts identical to the reference's.
+                const bool massless = STATS && (__double2hiint(c.w) | __double2loint(c.w)) == 0;
+                bool interact;
+                if (mt.y & NB_LEAF_FLAG) {
+                    interact = (mt.y & NB_PAYLOAD_MASK) != me && !massless;  // own leaf skipped (:349)
+                    next = cur + 1;
+                    if (STATS) nvis += interact ? 1u : 0u;
+                } else if (massless) {
+                    interact = false;
+                    next = max(mt.x, cur + 1);
+                } else {
+                    const uint32_t t = mt.y << 21;                       // depth << 21 (the rank bits shift out)
+                    const int diff = __double2hiint(D) - (W0 - (int) t);
+                    bool accept = diff > 0;
+                    if (t >= t_lim || (uint32_t) (diff + 1) <= 2u) {
+                        // undecided: the oracle's exact expression, no contraction
+                        const uint32_t depth = mt.y & NB_PAYLOAD_MASK;
+                        const double d2o = __dadd_rn(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)), __dmul_rn(dz, dz));
+                        const double rs = __ddiv_rn(1.0, __dsqrt_rn(d2o));
+                        accept = __dmul_rn(scale_pow2(edge0, depth), rs) < theta;
+                    }
+                    interact = accept;
+                    next = accept ? max(mt.x, cur + 1) : cur + 1;  // skip links always point forward
+                    if (STATS) nvis += 1u;
+                }
+                if (interact) {
+                    if (STATS) nacc += 1u;
+                    const double y0 = nb_rsqrt_seed(D);
+                    const double y2 = y0 * y0;
+                    const double e = fma(-D, y2, 1.0);
+                    const double y3 = y2 * y0;
+                    const double p = fma(1.875, e, 1.5);
+                    const double q = fma(p, e, 1.0);
+                    const double s = (y3 * c.w) * q;
+                    ax = fma(dx, s, ax);
+                    ay = fma(dy, s, ay);
+                    az = fma(dz, s, az);
+                }
+            }
+            cur = __reduce_min_sync(0xffffffffu, next);
+        }
+        if (valid) {
+            asx[b] = ax * G;
+            asy[b] = ay * G;
+            asz[b] = az * G;
+            if (STATS) visits[b] = nvis;
+        }
+        if (STATS) { nvis_w += nvis; nacc_w += nacc; }
+        if (!PERSIST) break;
+    }
+    if (STATS) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            nvis_w += __shfl_xor_sync(0xffffffffu, nvis_w, o);
+            nacc_w += __shfl_xor_sync(0xffffffffu, nacc_w, o);
+        }
+        if (lane == 0) { atomicAdd(&totals[0], nvis_w); atomicAdd(&totals[1], nacc_w); }
     }
 }
 
@@ -464,22 +614,43 @@ int nbk_bh_accel(nb_ctx *ctx, uint64_t s_begin, uint64_t s_end) {
     bh_traverse_kernel<ST, VV><<<grid, threads, 0, ctx->stream>>>(com, b.meta, b.dev_flags, ctx->n, b.aabb_dev, ctx->x, ctx->y, \
                                                                   ctx->z, s_begin, s_end, ctx->cfg.theta, ctx->cfg.epsilon2,  \
                                                                   ctx->cfg.G, ctx->ax, ctx->ay, ctx->az, b.visits, b.stat_totals)
+    // walk_variant (cfg.reserved[3]): 0 = production walk (integer-pipe acceptance test; SM-local tile queues from 2^19
+    // bodies per call, below that the tail of the persistent form costs more than its locality gains); 20 / 50 force
+    // the grid-mapped / persistent form; 1..9 = the earlier fp64-threshold walk and its variants, kept for A/B runs.
+#define NB_LAUNCH_IW(ST, PERSIST, GRID)                                                                                 \
+    bh_traverse_iw_kernel<ST, PERSIST><<<GRID, threads, 0, ctx->stream>>>(                                              \
+        com, b.meta, b.dev_flags, ctx->n, b.aabb_dev, ctx->x, ctx->y, ctx->z, s_begin, s_end, ctx->cfg.theta,           \
+        ctx->cfg.epsilon2, ctx->cfg.G, ctx->ax, ctx->ay, ctx->az, b.visits, b.stat_totals, b.dev_flags + 8,             \
+        (uint32_t) std::min<int>(ctx->sm_count, 1024))
+    const int wv = ctx->cfg.reserved[3];
     if (b.stats_enabled) {
         NB_CUDA(ctx, cudaMemsetAsync(b.stat_totals, 0, 8 * sizeof(unsigned long long), ctx->stream));
         NB_CUDA(ctx, cudaMemsetAsync(b.visits, 0, ctx->n * sizeof(uint32_t), ctx->stream));
-        NB_LAUNCH_WALK(true, 0);
-    } else {
-        switch (ctx->cfg.reserved[3]) {
+        if (wv >= 1 && wv <= 9) NB_LAUNCH_WALK(true, 0);
+        else NB_LAUNCH_IW(true, false, grid);
+    } else if (wv >= 1 && wv <= 9) {
+        switch (wv) {
             case 1: NB_LAUNCH_WALK(false, 1); break;
             case 2: NB_LAUNCH_WALK(false, 2); break;
             case 3: NB_LAUNCH_WALK(false, 3); break;
-            case 5: NB_LAUNCH_WALK(false, 5); break;
             case 7: NB_LAUNCH_WALK(false, 7); break;
             case 8: NB_LAUNCH_WALK(false, 0); break;
             case 9: NB_LAUNCH_WALK(false, 9); break;
-            default: NB_LAUNCH_WALK(false, 5); break;  // table-free thresholds, 48 registers (best of the sweep)
+            default: NB_LAUNCH_WALK(false, 5); break;  // table-free fp64 thresholds, 48 registers
         }
+    } else if (wv == 50 || (wv != 20 && count >= (1ull << 19))) {
+        if (b.walk_ctas_threads != threads) {   // resident CTAs per SM for this CTA size (queried once)
+            int per_sm = 0;
+            NB_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, bh_traverse_iw_kernel<false, true>, threads, 0));
+            b.walk_ctas_per_sm = per_sm < 1 ? 1 : per_sm;
+            b.walk_ctas_threads = threads;
+        }
+        NB_CUDA(ctx, cudaMemsetAsync(b.dev_flags + 8, 0, 1024 * sizeof(uint32_t), ctx->stream));
+        NB_LAUNCH_IW(false, true, std::min<unsigned>(grid, (unsigned) (b.walk_ctas_per_sm * ctx->sm_count)));
+    } else {
+        NB_LAUNCH_IW(false, false, grid);
     }
+#undef NB_LAUNCH_IW
 #undef NB_LAUNCH_WALK
     NB_LAUNCH_CHECK(ctx);
     return NB_OK;

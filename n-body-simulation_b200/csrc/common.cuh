@@ -48,6 +48,7 @@ struct nb_bh_state {
     // results
     uint32_t *visits = nullptr;                              // per-body visit counters (stats)
     unsigned long long *stat_totals = nullptr;               // {visits, accepts}
+    int walk_ctas_per_sm = 0, walk_ctas_threads = 0;         // occupancy of the persistent walk (cached)
     // device scalars
     double *aabb_dev = nullptr;                              // 7 doubles: min xyz, max xyz, edge
     double *aabb_partial = nullptr;

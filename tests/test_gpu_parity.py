@@ -339,6 +339,26 @@ def test_bh_accelerations_and_visit_counts(nb, oracle, n, gen, seed, theta):
     c.close()
 
 
+@pytest.mark.parametrize("n,gen", [(3000, "plummer"), (700000, "uniform_sphere")])
+def test_bh_walk_forms_agree(nb, oracle, n, gen):
+    """The production walk in its grid-mapped (20) and SM-queue (50) forms is the same arithmetic per body: bitwise equal
+    accelerations; the earlier fp64-threshold walk (5) differs only by the rounding of eps2 folded into the fma chain.
+    walk_variant 0 picks the form by size (SM queues from 2^19 bodies).  All forms must match the oracle."""
+    m, x, y, z, *_ = getattr(nb.generators, gen)(n, seed=21)
+    got = {}
+    for wv in (0, 5, 20, 50):
+        c = nb.Context(device=0, theta=0.5, walk_variant=wv)
+        c.set_bodies(m, x, y, z)
+        c.bh_build()
+        c.bh_accel()
+        got[wv] = np.stack(c.accelerations())
+        c.close()
+    assert np.array_equal(got[20], got[50]) and np.array_equal(got[0], got[20])
+    assert np.abs(got[5] - got[20]).max() <= 1e-13 * np.abs(got[20]).max()
+    want = oracle.Tree(m, x, y, z).accel(0.5)
+    assert relerr(tuple(got[0]), want) <= TOL
+
+
 @pytest.mark.parametrize("variant", [0, 3])
 def test_bh_massless_bodies_are_invisible(nb, oracle, variant):
     """The reference skips nodes with SUM_MASSES == 0 (BarnesHutAlgorithm.cpp:349): massless bodies exert no force and
