@@ -134,6 +134,8 @@ def default_config(**overrides):
             cfg.reserved[1] = int(v)
         elif k == "naive_segments":
             cfg.reserved[4] = int(v)
+        elif k == "walk_run_len":
+            cfg.reserved[5] = int(v)
         elif k == "walk_variant":
             cfg.reserved[3] = int(v)
         elif k == "naive_variant":

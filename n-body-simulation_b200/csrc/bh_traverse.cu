@@ -171,17 +171,20 @@ bh_traverse_kernel(const double4 *__restrict__ com, const uint2 *__restrict__ me
 //     (BarnesHutAlgorithm.cpp:355-359) with correctly rounded operations, so the decision is the reference's.  No
 //     per-depth fp64 thresholds, nothing spills under the 48-register budget (40 warps per SM);
 //   * PERSIST: the grid only fills the machine and every WARP draws 32-body tiles from a queue that belongs to the SM
-//     it runs on (the sorted body range is cut into one contiguous chunk per SM; a warp whose queue is empty steals
-//     from the following queues).  The ~40 warps resident on an SM therefore walk neighbouring bodies at the same time
-//     and share the node records they pull into that SM's L1 -- the hardware block scheduler would hand an SM blocks
-//     that are 148 blocks apart -- and no CTA is ever re-launched.  ncu at N = 2^24: L1 hit rate 65 % -> 73 %,
-//     warps active 57 % -> 62 %, 89.6 ms -> 85.1 ms.  tile_counters: one uint32 per queue, zeroed before the launch.
+//     it runs on (queue c owns runs of RUN consecutive tiles of the sorted order, interleaved with the other queues'
+//     runs; a warp whose queue is empty steals from the following queues).  The ~40 warps resident on an SM therefore
+//     walk neighbouring bodies at the same time and share the node records they pull into that SM's L1 -- the hardware
+//     block scheduler would hand an SM blocks that are 148 blocks apart -- while all SMs stay inside one moving window
+//     of the tree (L2), and no CTA is ever re-launched.  ncu at N = 2^24: L1 hit rate 65 % -> 73 %, warps active
+//     57 % -> 62 %, 89.6 ms -> 84.2 ms.  tile_counters: one uint32 per queue, zeroed before the launch.
+//     The queue bookkeeping must not add live values to the cursor loop: with RUN as a run-time argument ptxas spilled
+//     two loop invariants and the walk fell back to 90 ms, hence the template constant.
 // Explored on top of this and rejected (N = 2^24, theta = 0.5, all parity-green): issuing the next node's loads before
 // the force arithmetic (software pipelining: 95 ms, the 12 extra live registers cost 20 % of the resident warps);
-// prefetch.global.L1 of the next node (98-102 ms); ticketed one-tile-per-warp assignment (87 ms); interleaved runs of
-// tiles instead of contiguous chunks (no better than contiguous).
+// prefetch.global.L1 of the next node (98-102 ms); ticketed one-tile-per-warp assignment on a full grid (87 ms); one
+// straight-line accept/skip decision for leaves and cells instead of the leaf branch (88.9 ms).
 // ---------------------------------------------------------------------------------------------------------------------
-template <bool STATS, bool PERSIST>
+template <bool STATS, bool PERSIST, uint32_t RUN>
 __global__ void __launch_bounds__(256, 5)
 bh_traverse_iw_kernel(const double4 *__restrict__ com, const uint2 *__restrict__ meta, const uint32_t *__restrict__ flags,
                       uint64_t n_bodies, const double *__restrict__ aabb, const double *__restrict__ sx,
@@ -219,8 +222,13 @@ bh_traverse_iw_kernel(const double4 *__restrict__ com, const uint2 *__restrict__
                 uint32_t t = 0;
                 if (lane == 0) t = atomicAdd(&tile_counters[cidx], 1u);
                 t = __shfl_sync(0xffffffffu, t, 0);
-                tile = (uint64_t) cidx * T + t;
-                if (t < T && tile < tiles_total) { have = true; break; }
+                // RUN == 0: queue c is one contiguous chunk of T tiles; otherwise queue c owns runs of RUN consecutive
+                // tiles interleaved with the other queues' runs (its run r is run r*n_chunks + c of the sorted order),
+                // so all SMs stay inside one moving window of the tree (L2) while the warps of one SM walk
+                // neighbouring bodies (L1)
+                tile = RUN ? ((uint64_t) (t / (RUN ? RUN : 1u)) * n_chunks + cidx) * RUN + (t % (RUN ? RUN : 1u))
+                           : (uint64_t) cidx * T + t;
+                if ((RUN || t < T) && tile < tiles_total) { have = true; break; }
                 ++probe;   // this queue is empty for good: own queue first, then steal from the following ones
             }
             if (!have) break;
@@ -617,8 +625,8 @@ int nbk_bh_accel(nb_ctx *ctx, uint64_t s_begin, uint64_t s_end) {
     // walk_variant (cfg.reserved[3]): 0 = production walk (integer-pipe acceptance test; SM-local tile queues from 2^19
     // bodies per call, below that the tail of the persistent form costs more than its locality gains); 20 / 50 force
     // the grid-mapped / persistent form; 1..9 = the earlier fp64-threshold walk and its variants, kept for A/B runs.
-#define NB_LAUNCH_IW(ST, PERSIST, GRID)                                                                                 \
-    bh_traverse_iw_kernel<ST, PERSIST><<<GRID, threads, 0, ctx->stream>>>(                                              \
+#define NB_LAUNCH_IW(ST, PERSIST, RUN, GRID)                                                                            \
+    bh_traverse_iw_kernel<ST, PERSIST, RUN><<<GRID, threads, 0, ctx->stream>>>(                                         \
         com, b.meta, b.dev_flags, ctx->n, b.aabb_dev, ctx->x, ctx->y, ctx->z, s_begin, s_end, ctx->cfg.theta,           \
         ctx->cfg.epsilon2, ctx->cfg.G, ctx->ax, ctx->ay, ctx->az, b.visits, b.stat_totals, b.dev_flags + 8,             \
         (uint32_t) std::min<int>(ctx->sm_count, 1024))
@@ -627,7 +635,7 @@ int nbk_bh_accel(nb_ctx *ctx, uint64_t s_begin, uint64_t s_end) {
         NB_CUDA(ctx, cudaMemsetAsync(b.stat_totals, 0, 8 * sizeof(unsigned long long), ctx->stream));
         NB_CUDA(ctx, cudaMemsetAsync(b.visits, 0, ctx->n * sizeof(uint32_t), ctx->stream));
         if (wv >= 1 && wv <= 9) NB_LAUNCH_WALK(true, 0);
-        else NB_LAUNCH_IW(true, false, grid);
+        else NB_LAUNCH_IW(true, false, 0, grid);
     } else if (wv >= 1 && wv <= 9) {
         switch (wv) {
             case 1: NB_LAUNCH_WALK(false, 1); break;
@@ -641,14 +649,19 @@ int nbk_bh_accel(nb_ctx *ctx, uint64_t s_begin, uint64_t s_end) {
     } else if (wv == 50 || (wv != 20 && count >= (1ull << 19))) {
         if (b.walk_ctas_threads != threads) {   // resident CTAs per SM for this CTA size (queried once)
             int per_sm = 0;
-            NB_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, bh_traverse_iw_kernel<false, true>, threads, 0));
+            NB_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, bh_traverse_iw_kernel<false, true, 0>, threads, 0));
             b.walk_ctas_per_sm = per_sm < 1 ? 1 : per_sm;
             b.walk_ctas_threads = threads;
         }
         NB_CUDA(ctx, cudaMemsetAsync(b.dev_flags + 8, 0, 1024 * sizeof(uint32_t), ctx->stream));
-        NB_LAUNCH_IW(false, true, std::min<unsigned>(grid, (unsigned) (b.walk_ctas_per_sm * ctx->sm_count)));
+        const unsigned pg = std::min<unsigned>(grid, (unsigned) (b.walk_ctas_per_sm * ctx->sm_count));
+        // cfg.reserved[5] (walk_run_len): 0 = interleaved runs of 160 tiles per SM queue (84.2 ms at N = 2^24; 40 / 80 /
+        // 320 tiles measured 84.4 / 84.2 / 84.5), 1 = one contiguous chunk per SM (85.2 ms: L1 hit rate up, but 148
+        // distant windows at a time drop the L2 hit rate from 92 % to 71 %)
+        if (ctx->cfg.reserved[5] == 1) NB_LAUNCH_IW(false, true, 0, pg);
+        else NB_LAUNCH_IW(false, true, 160, pg);
     } else {
-        NB_LAUNCH_IW(false, false, grid);
+        NB_LAUNCH_IW(false, false, 0, grid);
     }
 #undef NB_LAUNCH_IW
 #undef NB_LAUNCH_WALK
