@@ -15,6 +15,8 @@ pytestmark = pytest.mark.gpu
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 EXE = os.path.join(ROOT, "n-body-simulation_b200", "N_Body_Simulation")
+# the reference's own main.cpp / writers / parser with its two back-end translation units replaced (integration/)
+HYBRID = os.path.join(ROOT, "integration", "_build", "N_Body_Simulation_b200")
 TOL = 1e-10
 CANON_KEYS = ("depth", "path_hi", "path_lo", "kind", "body", "count", "edge", "minx", "miny", "minz", "mass", "comx",
               "comy", "comz")
@@ -198,9 +200,9 @@ def test_barnes_hut_side_by_side(nb, ref, n, gen, seed, theta):
 
 
 # ---- executables: ours and the reference's on the same command line -----------------------------------------------------------
-def run_both(ref, tmp_path, fixture, flags):
+def run_both(ref, tmp_path, fixture, flags, ours=EXE):
     outs = []
-    for name, exe in (("ours", EXE), ("reference", ref.EXE_PATH)):
+    for name, exe in (("ours", ours), ("reference", ref.EXE_PATH)):
         out = tmp_path / name
         r = subprocess.run([exe, "--file=" + fixture, "--vs_dir=" + str(out)] + flags, capture_output=True, text=True,
                            timeout=900)
@@ -274,3 +276,31 @@ def test_times_json_has_the_reference_keys(nb, ref, tmp_path, golden_dir):
                 assert len(a[k]) == len(v), k         # one entry per step, as in the reference
             elif k != "device":
                 assert a[k] == v, k
+
+
+@pytest.mark.parametrize("algorithm,extra", [("naive", ["--opt_stage=2"]), ("BarnesHut", ["--theta=0.5"])])
+def test_reference_driver_on_top_of_the_c_abi(nb, ref, tmp_path, golden_dir, algorithm, extra):
+    """INTEGRATION.md section B as a running program: the reference's unmodified main.cpp, InputParser, TimeMeasurement
+    and generateParaViewOutput linked with integration/{Naive,BarnesHut}Algorithm_b200.cpp (the two replaced
+    translation units, compiled against the reference's unmodified headers) and libnbody_b200.so.  Its output files
+    equal those of the all-reference executable."""
+    if not os.path.exists(HYBRID):
+        pytest.skip("integration/_build is not built (needs /root/reference at build time)")
+    fixture = os.path.join(golden_dir, "solar_178.csv")
+    flags = ["--dt=1h", "--t_end=10d", "--vs=2d", "--algorithm=" + algorithm, "--energy=true"] + extra
+    (ours, out_o), (theirs, out_r) = run_both(ref, tmp_path, fixture, flags, ours=HYBRID)
+    names_o = sorted(f for f in os.listdir(ours) if f != "times.json")
+    names_r = sorted(f for f in os.listdir(theirs) if f != "times.json")
+    assert names_o == names_r and len(names_o) == 2 + 6
+    for f in names_o:
+        assert_same_text(os.path.join(ours, f), os.path.join(theirs, f), max_boundary_tokens=8)
+    assert [l for l in out_o.splitlines() if l.startswith("Finished")] == \
+           [l for l in out_r.splitlines() if l.startswith("Finished")]
+    import json
+    a = json.load(open(os.path.join(ours, "times.json")))
+    b = json.load(open(os.path.join(theirs, "times.json")))
+    assert set(a) == set(b)
+    assert "B200" in a["device"] and a["algorithm"] == b["algorithm"]
+    for k, v in b.items():
+        if isinstance(v, list):
+            assert len(a[k]) == len(v), k
