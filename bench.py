@@ -45,8 +45,8 @@ BH_BYTES_PER_VISIT = 40.0            # com xyz + mass (32 B) + skip/m
 BH_BYTES_PER_BODY = 48.0             # position in, acceleration out
 NAIVE_TILE = 256                     # --block_size used for the benchmark (shared-memory tile length)
 # dram__bytes_read.sum + dram__bytes_write.sum per launch from the `ncu --set full` captures summarised under profiles/
-# (naive: N = 2^20, profiles/naive_accel_r01.txt; Barnes-Hut walk: N = 2^22, profiles/bh_traverse_r01.txt)
-NCU_TRAFFIC_BYTES = {("naive", 1 << 20): 121.3425e6 + 55.0454e6, ("bh", 1 << 22): 400.5560e6 + 93.6484e6}
+# (naive: N = 2^20, profiles/naive_accel_r01b.txt; Barnes-Hut walk: N = 2^24, profiles/bh_traverse_r01b.txt)
+NCU_TRAFFIC_BYTES = {("naive", 1 << 20): 123.167744e6 + 55.533824e6, ("bh", 1 << 24): 2.580038e9 + 401.008896e6}
 
 
 def parse_args():
@@ -300,7 +300,7 @@ def measure_bh(nb, torch, dist, args, rank, local_rank, world, dev):
         "phases_ms": {k: round(v, 4) for k, v in timers.items() if v},
         "visits_per_body": visits / n, "accepts_per_body": accepts / n, "max_depth": int(info.max_depth),
         "internal_nodes_per_body": info.num_internal / n,
-        "roofline": {"bound": "hbm", "kernel": "bh_traverse_kernel", "achieved": achieved, "peak": hbm, "unit": "GB/s",
+        "roofline": {"bound": "hbm", "kernel": "bh_traverse_iw_kernel", "achieved": achieved, "peak": hbm, "unit": "GB/s",
                      "frac": achieved / hbm, "traffic": NCU_TRAFFIC_BYTES.get(("bh", n)) if world == 1 else None,
                      "peak_source": "measured" if "hbm_gbs" in peaks else "fallback",
                      "note": "algorithmic bytes = 40 B x non-empty visits + 48 B x bodies; warp-uniform node loads are "
