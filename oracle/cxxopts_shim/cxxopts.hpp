@@ -3,7 +3,8 @@
 // network here).  Supports: Options(name[, help]); add_options()(name, description, value<T>()) chains;
 // parse(argc, argv) with "--key=value", "--key value" and bare "--flag" (bool -> true); result.count(key);
 // result[key].as<T>() for std::string, int, unsigned, double, bool.  Unknown options and missing values throw, like
-// cxxopts does.
+// cxxopts does.  For dataset_converter/main_preprocess.cpp also: value<T>()->default_value("..."), "s,long" short
+// options, std::vector<std::string> values, parse_positional({...}), set_width / set_tab_expansion (formatting no-ops).
 #pragma once
 
 #include <map>
@@ -24,28 +25,48 @@ struct option_has_no_value : exception { using exception::exception; };
 struct incorrect_argument_type : exception { using exception::exception; };
 }  // namespace exceptions
 
-struct Value {
+struct Value : std::enable_shared_from_this<Value> {
     bool is_bool = false;
+    bool is_list = false;
+    bool has_default = false;
+    std::string default_text;
+    std::shared_ptr<Value> default_value(const std::string &text) {
+        has_default = true;
+        default_text = text;
+        return shared_from_this();
+    }
 };
+
+template<class T>
+struct is_string_vector : std::false_type {};
+template<>
+struct is_string_vector<std::vector<std::string>> : std::true_type {};
 
 template<class T>
 std::shared_ptr<Value> value() {
     auto v = std::make_shared<Value>();
     v->is_bool = std::is_same_v<T, bool>;
+    v->is_list = is_string_vector<T>::value;
     return v;
 }
 
 class OptionValue {
     std::string key, text;
-    bool present = false;
+    std::vector<std::string> items;
+    bool present = false, defaulted = false;
+    friend class Options;
 public:
     OptionValue() = default;
-    OptionValue(std::string k, std::string t) : key(std::move(k)), text(std::move(t)), present(true) {}
-    std::size_t count() const { return present ? 1 : 0; }
+    OptionValue(std::string k, std::string t, bool from_default = false)
+            : key(std::move(k)), text(std::move(t)), present(true), defaulted(from_default) { items.push_back(text); }
+    std::size_t count() const { return present && !defaulted ? items.size() : 0; }
 
     template<class T>
     T as() const {
         if (!present) throw exceptions::option_has_no_value("Option '" + key + "' has no value");
+        if constexpr (is_string_vector<T>::value) {
+            return items;
+        } else
         if constexpr (std::is_same_v<T, std::string>) {
             return text;
         } else if constexpr (std::is_same_v<T, bool>) {
@@ -66,6 +87,7 @@ class ParseResult {
     std::map<std::string, OptionValue> values;
     friend class Options;
 public:
+    ParseResult() = default;
     std::size_t count(const std::string &key) const {
         auto it = values.find(key);
         return it == values.end() ? 0 : it->second.count();
@@ -93,24 +115,43 @@ public:
 
 class Options {
     std::string program, description;
-    struct Spec { std::string description; bool is_bool; };
+    struct Spec { std::string description; bool is_bool; bool is_list; bool has_default; std::string default_text; };
     std::map<std::string, Spec> specs;
     std::map<std::string, std::string> short_to_long;
+    std::vector<std::string> positional;
     friend class OptionAdder;
 public:
     explicit Options(std::string name, std::string help = "") : program(std::move(name)), description(std::move(help)) {}
+
+    Options &set_width(std::size_t) { return *this; }
+    Options &set_tab_expansion(bool = true) { return *this; }
+    void parse_positional(std::initializer_list<std::string> names) { positional.assign(names.begin(), names.end()); }
 
     OptionAdder add_options(const std::string & = "") { return OptionAdder(*this); }
 
     ParseResult parse(int argc, const char *const *argv) const {
         ParseResult r;
+        for (const auto &kv: specs)
+            if (kv.second.has_default) r.values[kv.first] = OptionValue(kv.first, kv.second.default_text, true);
+        auto add = [&r, this](const std::string &key, const std::string &val) {
+            auto it = r.values.find(key);
+            if (specs.at(key).is_list && it != r.values.end() && !it->second.defaulted) it->second.items.push_back(val);
+            else r.values[key] = OptionValue(key, val);
+        };
+        std::size_t next_positional = 0;
         for (int i = 1; i < argc; ++i) {
             std::string arg = argv[i];
             if (arg.rfind("--", 0) != 0) {
                 if (arg.size() == 2 && arg[0] == '-' && short_to_long.count(arg.substr(1))) {
                     arg = "--" + short_to_long.at(arg.substr(1));
                 } else {
-                    continue;  // positional arguments are ignored (cxxopts collects them as unmatched)
+                    // positional: goes to the next name given to parse_positional (a list option takes all the rest)
+                    if (next_positional < positional.size()) {
+                        const std::string &key = positional[next_positional];
+                        add(key, arg);
+                        if (!specs.at(key).is_list) ++next_positional;
+                    }
+                    continue;
                 }
             }
             std::string key = arg.substr(2), val;
@@ -131,7 +172,7 @@ public:
                     val = argv[++i];
                 }
             }
-            r.values[key] = OptionValue(key, val);
+            add(key, val);
         }
         return r;
     }
@@ -152,7 +193,7 @@ inline OptionAdder &OptionAdder::operator()(const std::string &names, const std:
         longname = a.size() > b.size() ? a : b;
         owner.short_to_long[a.size() > b.size() ? b : a] = longname;
     }
-    owner.specs[longname] = Options::Spec{description, v->is_bool};
+    owner.specs[longname] = Options::Spec{description, v->is_bool, v->is_list, v->has_default, v->default_text};
     return *this;
 }
 
