@@ -116,6 +116,15 @@ int nb_leapfrog_part1(nb_ctx *ctx, double dt);
 int nb_leapfrog_part2(nb_ctx *ctx, double dt);
 /* part 2 of step k immediately followed by part 1 of step k+1 in one pass (non-visualised steps).         */
 int nb_leapfrog_part2_part1(nb_ctx *ctx, double dt);
+/* `nsteps` complete leapfrog steps of the reference's time loop without output in between
+ * (NaiveAlgorithm.cpp:131-258 / BarnesHutAlgorithm.cpp:149-276 for steps that are not visualised):
+ *     per step: part 1; force evaluation (algorithm 0 = naive, 1 = Barnes-Hut build + traversal); part 2.
+ * Accelerations of the current positions must be on the device (as after any force call).  Bit-identical to issuing
+ * the calls one by one.  On one GPU the inner steps are replayed from a CUDA graph (the small-N time loop is launch
+ * bound: one Barnes-Hut step is ~90 kernel launches).  ms (optional, NB_T_COUNT entries): phase times of the first
+ * step of the batch, measured with events when timers are enabled -- a sample, the replayed steps are not timed
+ * individually.  Asynchronous unless ms is requested.                                                            */
+int nb_advance(nb_ctx *ctx, int algorithm, double dt, uint32_t nsteps, double *ms);
 
 /* ---- energy ------------------------------------------------------------------------------------------------ */
 /* nBodyAlgorithm::computeEnergy (nBodyAlgorithm.hpp:91-97, .cpp:11-86).

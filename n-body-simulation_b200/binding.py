@@ -46,7 +46,7 @@ EXPORTED_SYMBOLS = [
     "nb_config_default", "nb_abi_version", "nb_status_string", "nb_create", "nb_destroy", "nb_last_error",
     "nb_synchronize", "nb_device_name", "nb_set_theta", "nb_set_block_size", "nb_set_sort_bodies",
     "nb_set_precise_rsqrt", "nb_set_bodies", "nb_set_positions", "nb_num_bodies", "nb_naive_accel", "nb_bh_build",
-    "nb_bh_accel", "nb_leapfrog_part1", "nb_leapfrog_part2", "nb_leapfrog_part2_part1", "nb_energy",
+    "nb_bh_accel", "nb_leapfrog_part1", "nb_leapfrog_part2", "nb_leapfrog_part2_part1", "nb_advance", "nb_energy",
     "nb_get_positions", "nb_get_velocities", "nb_get_accelerations", "nb_get_acceleration_norms",
     "nb_op_naive_accelerations", "nb_op_barnes_hut_accelerations", "nb_bh_tree_info", "nb_bh_aabb",
     "nb_bh_export_canonical", "nb_bh_sorted_bodies", "nb_bh_enable_stats", "nb_bh_get_stats",
@@ -93,6 +93,7 @@ def load_library():
         getattr(L, f).argtypes = [vp]
     for f in ("nb_leapfrog_part1", "nb_leapfrog_part2", "nb_leapfrog_part2_part1"):
         getattr(L, f).argtypes = [vp, C.c_double]
+    L.nb_advance.argtypes = [vp, C.c_int, C.c_double, C.c_uint32, _dp]
     L.nb_energy.argtypes = [vp, _dp]
     for f in ("nb_get_positions", "nb_get_velocities", "nb_get_accelerations"):
         getattr(L, f).argtypes = [vp, _dp, _dp, _dp]
@@ -263,6 +264,12 @@ class Context:
 
     def leapfrog_part2(self, dt):
         self._ck(self.L.nb_leapfrog_part2(self.h, dt))
+
+    def advance(self, algorithm, dt, nsteps, timers=False):
+        """nsteps complete leapfrog steps (part 1, forces, part 2 each); algorithm: "naive" or "BarnesHut"."""
+        ms = (C.c_double * 16)() if timers else None
+        self._ck(self.L.nb_advance(self.h, {"naive": 0, "BarnesHut": 1}[algorithm], dt, nsteps, ms))
+        return list(ms) if timers else None
 
     def leapfrog_part2_part1(self, dt):
         self._ck(self.L.nb_leapfrog_part2_part1(self.h, dt))

@@ -10,6 +10,8 @@
 
 #include "common.cuh"
 
+#include <cstring>
+
 int nbk_comm_allreduce_sum(nb_ctx *ctx, double *buf, size_t count);
 
 int nb_fail(nb_ctx *ctx, int status, const char *fmt, ...) {
@@ -94,6 +96,7 @@ int nb_create(const nb_config *cfg, nb_ctx **out) {
 }
 
 void nb_destroy(nb_ctx *ctx) {
+    if (ctx && ctx->step_graph) { cudaGraphExecDestroy(ctx->step_graph); ctx->step_graph = nullptr; }
     if (!ctx) return;
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
@@ -270,6 +273,120 @@ int nb_leapfrog_part2_part1(nb_ctx *ctx, double dt) {
     nb_timer_scope t(ctx, NB_T_LEAPFROG1);
     ctx->bh.built = false;
     return nbk_leapfrog_part2_part1(ctx, dt);
+}
+
+// ---- nb_advance: batches of steps, inner steps replayed from a CUDA graph --------------------------------------------
+static void drop_step_graph(nb_ctx *ctx) {
+    if (ctx->step_graph) cudaGraphExecDestroy(ctx->step_graph);
+    ctx->step_graph = nullptr;
+    ctx->graph_algorithm = -1;
+}
+
+static void state_pointers(const nb_ctx *ctx, const void *p[8]) {
+    p[0] = ctx->m; p[1] = ctx->x; p[2] = ctx->vx; p[3] = ctx->ax; p[4] = ctx->id; p[5] = ctx->bh.key_hi;
+    p[6] = ctx->bh.perm; p[7] = ctx->src;
+}
+
+// one inner step: closing half-kick of the previous step fused with kick-drift of the next, then the forces
+static int inner_step(nb_ctx *ctx, int algorithm, double dt) {
+    NB_CHECK(nb_leapfrog_part2_part1(ctx, dt));
+    if (algorithm == 0) return nb_naive_accel(ctx);
+    NB_CHECK(nb_bh_build(ctx));
+    return nb_bh_accel(ctx);
+}
+
+static bool graph_matches(const nb_ctx *ctx, int algorithm, double dt) {
+    if (!ctx->step_graph || ctx->graph_algorithm != algorithm || ctx->graph_dt != dt || ctx->graph_n != ctx->n) return false;
+    if (memcmp(&ctx->graph_cfg, &ctx->cfg, sizeof(nb_config)) != 0) return false;
+    const void *p[8];
+    state_pointers(ctx, p);
+    return memcmp(p, ctx->graph_ptrs, sizeof p) == 0;
+}
+
+// captures two inner steps; on success the host-side state (pointer roles) is back where it started
+static int capture_step_graph(nb_ctx *ctx, int algorithm, double dt) {
+    drop_step_graph(ctx);
+    const void *before[8], *after[8];
+    state_pointers(ctx, before);
+    const bool timers = ctx->timers_enabled;
+    const uint64_t launches0 = ctx->launches;
+    ctx->timers_enabled = false;   // no event records inside the graph
+    cudaGraph_t graph = nullptr;
+    cudaError_t e = cudaStreamBeginCapture(ctx->stream, cudaStreamCaptureModeThreadLocal);
+    int rc = NB_OK;
+    if (e == cudaSuccess) {
+        rc = inner_step(ctx, algorithm, dt);
+        if (rc == NB_OK) rc = inner_step(ctx, algorithm, dt);
+        e = cudaStreamEndCapture(ctx->stream, &graph);
+    }
+    ctx->timers_enabled = timers;
+    ctx->graph_launches = ctx->launches - launches0;
+    ctx->launches = launches0;     // nothing ran yet
+    state_pointers(ctx, after);
+    if (e != cudaSuccess || rc != NB_OK || !graph || memcmp(before, after, sizeof before) != 0) {
+        if (graph) cudaGraphDestroy(graph);
+        cudaGetLastError();
+        ctx->graph_unusable = true;
+        if (memcmp(before, after, sizeof before) != 0)
+            return nb_fail(ctx, NB_ERR_CUDA, "nb_advance: state pointers are not periodic over two steps");
+        return rc != NB_OK ? rc : NB_OK;   // fall back to the eager path
+    }
+    e = cudaGraphInstantiate(&ctx->step_graph, graph, 0);
+    cudaGraphDestroy(graph);
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        ctx->step_graph = nullptr;
+        ctx->graph_unusable = true;
+        return NB_OK;
+    }
+    ctx->graph_algorithm = algorithm;
+    ctx->graph_dt = dt;
+    ctx->graph_n = ctx->n;
+    ctx->graph_cfg = ctx->cfg;
+    memcpy(ctx->graph_ptrs, before, sizeof before);
+    return NB_OK;
+}
+
+int nb_advance(nb_ctx *ctx, int algorithm, double dt, uint32_t nsteps, double *ms) {
+    if (!ctx || !ctx->n) return nb_fail(ctx, NB_ERR_INVALID, "nb_advance: no bodies");
+    if (algorithm != 0 && algorithm != 1) return nb_fail(ctx, NB_ERR_INVALID, "nb_advance: algorithm must be 0 (naive) or 1 (Barnes-Hut)");
+    if (ms) for (int i = 0; i < NB_T_COUNT; ++i) ms[i] = 0;
+    if (nsteps == 0) return NB_OK;
+    NB_CUDA(ctx, cudaSetDevice(ctx->device));
+    // first step, eager and timed: part 1 + forces (its closing half-kick rides with the next step's part 1)
+    NB_CHECK(nb_leapfrog_part1(ctx, dt));
+    if (algorithm == 0) {
+        NB_CHECK(nb_naive_accel(ctx));
+    } else {
+        NB_CHECK(nb_bh_build(ctx));
+        NB_CHECK(nb_bh_accel(ctx));
+    }
+    if (ms && ctx->timers_enabled) NB_CHECK(nb_get_timers(ctx, ms));
+    uint32_t rest = nsteps - 1;
+    // pairs of inner steps from the graph: one GPU, no instrumentation, and enough steps to repay the capture
+    const bool graph_ok = ctx->world == 1 && !ctx->bh.stats_enabled && !ctx->graph_unusable;
+    if (graph_ok && rest >= 4) {
+        if (!graph_matches(ctx, algorithm, dt)) NB_CHECK(capture_step_graph(ctx, algorithm, dt));
+        while (ctx->step_graph && rest >= 2) {
+            NB_CUDA(ctx, cudaGraphLaunch(ctx->step_graph, ctx->stream));
+            ctx->launches += ctx->graph_launches;
+            rest -= 2;
+        }
+        if (algorithm == 1) ctx->bh.built = true;
+    }
+    const bool timers = ctx->timers_enabled;
+    ctx->timers_enabled = false;   // keep the sample of the first step
+    int rc = NB_OK;
+    for (; rest > 0 && rc == NB_OK; --rest) rc = inner_step(ctx, algorithm, dt);
+    ctx->timers_enabled = timers;
+    NB_CHECK(rc);
+    NB_CHECK(nb_leapfrog_part2(ctx, dt));
+    if (ms && ctx->timers_enabled) {   // Leapfrog Part 2 of the batch's last step
+        double tail[NB_T_COUNT];
+        NB_CHECK(nb_get_timers(ctx, tail));
+        ms[NB_T_LEAPFROG2] = tail[NB_T_LEAPFROG2];
+    }
+    return NB_OK;
 }
 
 int nb_energy(nb_ctx *ctx, double out[4]) {

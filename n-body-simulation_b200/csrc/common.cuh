@@ -94,6 +94,16 @@ struct nb_ctx {
     bool ev_valid[NB_T_COUNT] = {};
     uint64_t launches = 0;
     cudaEvent_t user_ev[8] = {};
+    // nb_advance: CUDA graph of two consecutive inner steps (the Barnes-Hut build swaps the state with its ping-pong
+    // partners once per step, so the pointer configuration has period two)
+    cudaGraphExec_t step_graph = nullptr;
+    int graph_algorithm = -1;
+    double graph_dt = 0;
+    uint64_t graph_n = 0;
+    nb_config graph_cfg = {};
+    const void *graph_ptrs[8] = {};
+    uint64_t graph_launches = 0;      // kernel launches one replay stands for
+    bool graph_unusable = false;      // the period-two assumption did not hold: stay on the eager path
     // comm
     void *nccl_comm = nullptr;
     int world = 1, rank = 0;

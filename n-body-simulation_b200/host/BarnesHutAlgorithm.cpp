@@ -38,11 +38,8 @@ void BarnesHutAlgorithm::startSimulation(const SimulationData &simulationData) {
         timer.addTimingSequence(name);
     const bool sorted = configuration::barnes_hut_algorithm::sortBodies;
     if (sorted) timer.addTimingSequence("Sort bodies");
-    runTimeLoop(simulationData, [this, sorted]() {
-        octree.buildOctree(timer);
-        computeAccelerations();
-        double ms[NB_T_COUNT];
-        check(nb_get_timers(ctx, ms), "nb_get_timers");
+    batchAlgorithm = 1;
+    recordForceTimers = [this, sorted](const double *ms) {
         timer.addTimeToSequence("Octree creation", ms[NB_T_TREE_TOTAL]);
         timer.addTimeToSequence("Acceleration Kernel Time", ms[NB_T_ACCEL]);
         timer.addTimeToSequence("Total Time", ms[NB_T_TREE_TOTAL] + ms[NB_T_ACCEL]);
@@ -53,5 +50,12 @@ void BarnesHutAlgorithm::startSimulation(const SimulationData &simulationData) {
         timer.addTimeToSequence("Build octree to level", 0.0);
         timer.addTimeToSequence("Prepare subtrees", 0.0);
         if (sorted) timer.addTimeToSequence("Sort bodies", 0.0);
+    };
+    runTimeLoop(simulationData, [this]() {
+        octree.buildOctree(timer);
+        computeAccelerations();
+        double ms[NB_T_COUNT];
+        check(nb_get_timers(ctx, ms), "nb_get_timers");
+        recordForceTimers(ms);
     });
 }

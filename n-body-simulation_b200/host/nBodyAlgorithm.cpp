@@ -138,6 +138,29 @@ void nBodyAlgorithm::runTimeLoop(const SimulationData &d, const std::function<vo
     while (time <= t_end + 0.000001) {
         const bool visualizeCurrentStep = std::abs(timeSinceLastVisualization - visualizationStepWidth) < 0.000001;
 
+        // A run of steps without output is handed to the device as one batch (nb_advance: inner steps replayed from a
+        // CUDA graph, the time loop of a small system is launch bound).  The run is found by stepping the two time
+        // accumulators exactly as the loop would, so the visualisation decisions are bit for bit the reference's.
+        if (!visualizeCurrentStep && !kickPending && batchAlgorithm >= 0) {
+            unsigned run = 0;
+            double t = time, since = timeSinceLastVisualization;
+            while (t <= t_end + 0.000001 && !(std::abs(since - visualizationStepWidth) < 0.000001) && run < 4096) {
+                ++run; t += dt; since += dt;
+            }
+            if (run >= 6) {
+                check(nb_advance(ctx, batchAlgorithm, dt, run, ms), "nb_advance");
+                for (unsigned k = 0; k < run; ++k) {
+                    recordForceTimers(ms);
+                    timer.addTimeToSequence("Leapfrog Part 1", ms[NB_T_LEAPFROG1]);
+                    timer.addTimeToSequence("Leapfrog Part 2", ms[NB_T_LEAPFROG2]);
+                }
+                completedTime = t - dt;
+                time = t;
+                timeSinceLastVisualization = since;
+                continue;
+            }
+        }
+
         // kick-drift; when the previous step needed no output its closing half-kick rides along in the same pass
         check(kickPending ? nb_leapfrog_part2_part1(ctx, dt) : nb_leapfrog_part1(ctx, dt), "leapfrog part 1");
         kickPending = false;

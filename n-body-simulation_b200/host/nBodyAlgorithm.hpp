@@ -95,4 +95,8 @@ protected:
     // the time loop shared by both back ends (reference NaiveAlgorithm.cpp:82-259 = BarnesHutAlgorithm.cpp:102-277);
     // `forces` evaluates the accelerations of the current positions and records its own timing sequences
     void runTimeLoop(const SimulationData &simulationData, const std::function<void()> &forces);
+    // set by the back end before runTimeLoop: the nb_advance algorithm id of `forces` (0 naive, 1 Barnes-Hut; -1 = never
+    // batch) and the part of `forces` that appends one entry to each of its timing sequences from a timer array
+    int batchAlgorithm = -1;
+    std::function<void(const double *)> recordForceTimers;
 };

@@ -495,6 +495,44 @@ def test_trajectory_naive_100_steps(nb, oracle):
     assert np.allclose(snaps["anorm"][-1], ref["anorm"][-1], rtol=1e-8, atol=0)
 
 
+@pytest.mark.parametrize("algorithm,n", [("naive", 300), ("BarnesHut", 300), ("BarnesHut", 20000)])
+@pytest.mark.parametrize("timers", [False, True])
+def test_advance_equals_single_steps(nb, algorithm, n, timers):
+    """nb_advance (batch of steps, inner steps replayed from a CUDA graph of two steps) is bit-identical to issuing
+    part 1 / forces / part 2 one by one, for any batch length, also across repeated batches (graph reuse) and after the
+    configuration changed in between (graph re-capture)."""
+    m, x, y, z, vx, vy, vz = nb.generators.plummer(n, seed=31)
+    dt = 1.0 / 24
+
+    def forces(c):
+        if algorithm == "naive":
+            c.naive_accel()
+        else:
+            c.bh_build(); c.bh_accel()
+
+    a = nb.Context(device=0, theta=0.6)
+    b = nb.Context(device=0, theta=0.6)
+    for c in (a, b):
+        c.set_bodies(m, x, y, z, vx, vy, vz)
+        c.enable_timers(timers)
+        forces(c)
+    total = 0
+    for k in (1, 2, 5, 6, 13, 40, 7):
+        if k == 13:   # a configuration change invalidates the captured graph
+            a.set_theta(0.45); b.set_theta(0.45)
+        ms = a.advance(algorithm, dt, k, timers=timers)
+        for _ in range(k):
+            b.leapfrog_part1(dt); forces(b); b.leapfrog_part2(dt)
+        total += k
+        for ga, gb in zip(a.positions() + a.velocities() + a.accelerations(), b.positions() + b.velocities() + b.accelerations()):
+            assert np.array_equal(ga, gb), (k, total)
+        if timers:
+            assert ms[0] > 0 and ms[1] > 0 and ms[2] > 0    # acceleration, leapfrog 1, leapfrog 2 of the sampled step
+    # the graph stands for real launches: same count as the eager sequence, within the fused half-kicks
+    assert abs(a.launch_count() - b.launch_count()) <= 2 * total
+    a.close(); b.close()
+
+
 def test_trajectory_barnes_hut(nb, oracle):
     m, x, y, z, vx, vy, vz = nb.generators.plummer(2048, seed=15)
     dt, K = 1.0 / 24, 40
