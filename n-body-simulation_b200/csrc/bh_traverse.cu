@@ -10,10 +10,11 @@
 //     same order (no warp-vote widening of the acceptance test), but node loads are warp-uniform broadcasts;
 //   * bodies are processed in sorted (Morton / DFS) order so neighbouring lanes share almost all of their lists;
 //   * centre of mass is pre-divided in the COM pass (same IEEE quotient the reference computes per visit);
-//   * acceptance test edge*rsqrt(d2) < theta is decided by two compares of d2 against per-depth thresholds
-//     ((edge/theta)^2 widened by 1e-12, scaled by 4^-depth with exponent arithmetic: no table, no memory access); the
-//     vanishing band in between is re-evaluated with correctly rounded sqrt / reciprocal / multiply, i.e. exactly the
-//     oracle's expression, so the interaction set is identical;
+//   * acceptance test edge*rsqrt(d2) < theta is decided without memory access from the node's depth: the production
+//     kernel (bh_traverse_iw_kernel) compares the high word of d2 + eps2 with hiword((edge_0/theta)^2) - (depth << 21)
+//     on the integer pipe; the vanishing band around the threshold is re-evaluated with correctly rounded sqrt /
+//     reciprocal / multiply, i.e. exactly the oracle's expression, so the interaction set is identical;
+//   * production launches are persistent: warps draw 32-body tiles from SM-local queues (see the kernel's comment);
 //   * force: MUFU.RSQ64H seed + cubic Taylor refinement of (d2+eps2)^(-3/2) (see naive.cu).
 // Payload per visited node: 32 B {com xyz, mass} + 8 B {skip, leaf|body / depth} = 40 B.
 #include "common.cuh"
@@ -29,21 +30,19 @@ __device__ __forceinline__ double scale_pow4(double v, uint32_t depth) {
     return __hiloint2double(__double2hiint(v) - (int) (depth << 21), __double2loint(v));
 }
 
-// V bit 0: thresholds by exponent arithmetic instead of shared-memory tables; bit 1: prefetch the DFS successor
 __device__ __forceinline__ double scale_pow2(double v, uint32_t depth) {  // v * 2^-depth, exact
     return __hiloint2double(__double2hiint(v) - (int) (depth << 20), __double2loint(v));
 }
 
-template <bool STATS, int V>
-__global__ void __launch_bounds__(256, (V & 8) ? 6 : ((V & 4) ? 5 : 1))
+// The earlier walk (walk_variant 5, kept for A/B runs): acceptance by two fp64 compares of d2 against per-depth
+// thresholds ((edge/theta)^2 widened by 1e-12, scaled by 4^-depth with exponent arithmetic), grid-mapped tiles.
+template <bool STATS>
+__global__ void __launch_bounds__(256, 5)
 bh_traverse_kernel(const double4 *__restrict__ com, const uint2 *__restrict__ meta, const uint32_t *__restrict__ flags,
                    uint64_t n_bodies, const double *__restrict__ aabb, const double *__restrict__ sx,
                    const double *__restrict__ sy, const double *__restrict__ sz, uint64_t s_begin, uint64_t s_end,
                    double theta, double eps2, double G, double *__restrict__ asx, double *__restrict__ asy,
                    double *__restrict__ asz, uint32_t *__restrict__ visits, unsigned long long *__restrict__ totals) {
-    constexpr bool TABLE_FREE = (V & 1) != 0;
-    constexpr bool PREFETCH = (V & 2) != 0;
-    __shared__ double t_hi[TABLE_FREE ? 1 : NB_BH_MAX_LEVELS], t_lo[TABLE_FREE ? 1 : NB_BH_MAX_LEVELS];
     const double edge0 = aabb[6];
     // accept <=> d2 > (edge/theta)^2; a depth-d cell scales the root thresholds by 4^-d exactly (the edge is halved
     // exactly per level, ParallelOctreeTopDownSubtrees.cpp:256)
@@ -51,15 +50,6 @@ bh_traverse_kernel(const double4 *__restrict__ com, const uint2 *__restrict__ me
     const bool scalable = ratio0 > 1e-200 && ratio0 < 1e200;  // theta == 0 or absurd boxes: always take the exact branch
     const double hi0 = scalable ? ratio0 * (1.0 + 1e-12) : __longlong_as_double(0x7ff0000000000000ll);
     const double lo0 = scalable ? ratio0 * (1.0 - 1e-12) : 0.0;
-    if (!TABLE_FREE) {
-        for (int t = threadIdx.x; t < NB_BH_MAX_LEVELS; t += blockDim.x) {
-            const double e = ldexp(edge0, -t);
-            const double ratio = (e / theta) * (e / theta);
-            t_hi[t] = ratio * (1.0 + 1e-12);
-            t_lo[t] = ratio * (1.0 - 1e-12);
-        }
-        __syncthreads();
-    }
     const uint32_t n_nodes = (uint32_t) n_bodies + flags[1];
     const int lane = threadIdx.x & 31;
     const uint64_t warp_global = ((uint64_t) blockIdx.x * blockDim.x + threadIdx.x) >> 5;
@@ -74,26 +64,12 @@ bh_traverse_kernel(const double4 *__restrict__ com, const uint2 *__restrict__ me
     uint32_t nvis = 0, nacc = 0;
 
     uint32_t cur = __reduce_min_sync(0xffffffffu, next);
-    double4 c = make_double4(0, 0, 0, 0), c_n = c;
-    uint2 mt = make_uint2(0, 0), mt_n = mt;
-    if (PREFETCH && cur < n_nodes) { c = com[cur]; mt = meta[cur]; }
     while (cur < n_nodes) {
-        if (PREFETCH) {
-            // speculative: the DFS successor is the next cursor whenever a lane opens `cur` or `cur` is a leaf
-            const uint32_t succ = cur + 1 < n_nodes ? cur + 1 : cur;
-            c_n = com[succ];
-            mt_n = meta[succ];
-        } else {
-            c = com[cur];   // warp-uniform address: one broadcast transaction
-            mt = meta[cur];
-        }
         if (next == cur) {
+            const double4 c = com[cur];   // warp-uniform address: one broadcast transaction
+            const uint2 mt = meta[cur];
             const double dx = c.x - px, dy = c.y - py, dz = c.z - pz;
             const double d2 = fma(dz, dz, fma(dy, dy, dx * dx));
-            // SUM_MASSES == 0 nodes are invisible in the reference (BarnesHutAlgorithm.cpp:349): massless bodies, and
-            // cells that hold only massless bodies, are neither counted nor opened.  Their contribution is exactly
-            // 0.0 either way (the build stores a finite record for them), so only the instrumented build pays for the
-            // check that keeps the visit counts identical to the reference's.
             const bool massless = STATS && (__double2hiint(c.w) | __double2loint(c.w)) == 0;
             bool interact;
             if (mt.y & NB_LEAF_FLAG) {
@@ -105,8 +81,8 @@ bh_traverse_kernel(const double4 *__restrict__ com, const uint2 *__restrict__ me
                 next = max(mt.x, cur + 1);
             } else {
                 const uint32_t depth = mt.y & NB_PAYLOAD_MASK;
-                bool accept = d2 > (TABLE_FREE ? scale_pow4(hi0, depth) : t_hi[depth]);
-                if (!accept && !(d2 < (TABLE_FREE ? scale_pow4(lo0, depth) : t_lo[depth]))) {
+                bool accept = d2 > scale_pow4(hi0, depth);
+                if (!accept && !(d2 < scale_pow4(lo0, depth))) {
                     // borderline: the oracle's exact expression (BarnesHutAlgorithm.cpp:355-359), no contraction
                     const double d2o = __dadd_rn(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)), __dmul_rn(dz, dz));
                     const double rs = __ddiv_rn(1.0, __dsqrt_rn(d2o));
@@ -131,15 +107,7 @@ bh_traverse_kernel(const double4 *__restrict__ com, const uint2 *__restrict__ me
                 az = fma(dz, s, az);
             }
         }
-        const uint32_t ncur = __reduce_min_sync(0xffffffffu, next);
-        if (PREFETCH) {
-            if (ncur == cur + 1) {
-                c = c_n; mt = mt_n;
-            } else if (ncur < n_nodes) {
-                c = com[ncur]; mt = meta[ncur];
-            }
-        }
-        cur = ncur;
+        cur = __reduce_min_sync(0xffffffffu, next);
     }
     if (valid) {
         asx[b] = ax * G;
@@ -618,13 +586,13 @@ int nbk_bh_accel(nb_ctx *ctx, uint64_t s_begin, uint64_t s_end) {
         NB_LAUNCH_CHECK(ctx);
         return NB_OK;
     }
-#define NB_LAUNCH_WALK(ST, VV)                                                                                          \
-    bh_traverse_kernel<ST, VV><<<grid, threads, 0, ctx->stream>>>(com, b.meta, b.dev_flags, ctx->n, b.aabb_dev, ctx->x, ctx->y, \
+#define NB_LAUNCH_WALK(ST)                                                                                              \
+    bh_traverse_kernel<ST><<<grid, threads, 0, ctx->stream>>>(com, b.meta, b.dev_flags, ctx->n, b.aabb_dev, ctx->x, ctx->y, \
                                                                   ctx->z, s_begin, s_end, ctx->cfg.theta, ctx->cfg.epsilon2,  \
                                                                   ctx->cfg.G, ctx->ax, ctx->ay, ctx->az, b.visits, b.stat_totals)
     // walk_variant (cfg.reserved[3]): 0 = production walk (integer-pipe acceptance test; SM-local tile queues from 2^19
     // bodies per call, below that the tail of the persistent form costs more than its locality gains); 20 / 50 force
-    // the grid-mapped / persistent form; 1..9 = the earlier fp64-threshold walk and its variants, kept for A/B runs.
+    // the grid-mapped / persistent form; 5 = the earlier fp64-threshold walk, kept for A/B runs.
 #define NB_LAUNCH_IW(ST, PERSIST, RUN, GRID)                                                                            \
     bh_traverse_iw_kernel<ST, PERSIST, RUN><<<GRID, threads, 0, ctx->stream>>>(                                         \
         com, b.meta, b.dev_flags, ctx->n, b.aabb_dev, ctx->x, ctx->y, ctx->z, s_begin, s_end, ctx->cfg.theta,           \
@@ -634,18 +602,10 @@ int nbk_bh_accel(nb_ctx *ctx, uint64_t s_begin, uint64_t s_end) {
     if (b.stats_enabled) {
         NB_CUDA(ctx, cudaMemsetAsync(b.stat_totals, 0, 8 * sizeof(unsigned long long), ctx->stream));
         NB_CUDA(ctx, cudaMemsetAsync(b.visits, 0, ctx->n * sizeof(uint32_t), ctx->stream));
-        if (wv >= 1 && wv <= 9) NB_LAUNCH_WALK(true, 0);
+        if (wv == 5) NB_LAUNCH_WALK(true);
         else NB_LAUNCH_IW(true, false, 0, grid);
-    } else if (wv >= 1 && wv <= 9) {
-        switch (wv) {
-            case 1: NB_LAUNCH_WALK(false, 1); break;
-            case 2: NB_LAUNCH_WALK(false, 2); break;
-            case 3: NB_LAUNCH_WALK(false, 3); break;
-            case 7: NB_LAUNCH_WALK(false, 7); break;
-            case 8: NB_LAUNCH_WALK(false, 0); break;
-            case 9: NB_LAUNCH_WALK(false, 9); break;
-            default: NB_LAUNCH_WALK(false, 5); break;  // table-free fp64 thresholds, 48 registers
-        }
+    } else if (wv == 5) {
+        NB_LAUNCH_WALK(false);
     } else if (wv == 50 || (wv != 20 && count >= (1ull << 19))) {
         if (b.walk_ctas_threads != threads) {   // resident CTAs per SM for this CTA size (queried once)
             int per_sm = 0;
