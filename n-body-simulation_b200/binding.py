@@ -137,6 +137,8 @@ def default_config(**overrides):
             cfg.reserved[4] = int(v)
         elif k == "walk_run_len":
             cfg.reserved[5] = int(v)
+        elif k == "sort_variant":
+            cfg.reserved[6] = int(v)
         elif k == "walk_variant":
             cfg.reserved[3] = int(v)
         elif k == "naive_variant":

@@ -475,7 +475,7 @@ int nbk_bh_reserve(nb_ctx *ctx) {
     NB_CHECK(nb_alloc(ctx, &b.level, 3 * NB_LEVELS));
     NB_CHECK(nb_alloc(ctx, &b.level_list, cap_nodes - n + 8));
     NB_CHECK(nb_alloc(ctx, &b.body_count, cap_nodes));
-    const size_t scratch = nbprim::rs_scratch_elems(nb) + nbprim::scan_tiles_for(nb) + 64;
+    const size_t scratch = std::max(nbprim::rs_scratch_elems(nb), nbprim::os_scratch_elems(nb)) + nbprim::scan_tiles_for(nb) + 64;
     NB_CHECK(nb_alloc(ctx, &b.hist, scratch));
     NB_CHECK(nb_alloc(ctx, &b.aabb_dev, 8));
     NB_CHECK(nb_alloc(ctx, &b.aabb_partial, 6 * 1024));
@@ -533,8 +533,14 @@ int nbk_bh_build(nb_ctx *ctx) {
         nb_timer_scope t(ctx, NB_T_KEYS_SORT);
         keys_kernel<<<g256, 256, 0, ctx->stream>>>(ctx->x, ctx->y, ctx->z, n, b.aabb_dev, b.key_hi);
         NB_LAUNCH_CHECK(ctx);
-        NB_CHECK(nbprim::radix_sort_pairs(ctx, b.key_hi, b.perm, b.key_hi_alt, b.perm_alt, n, 63, b.hist, &hi_sorted,
-                                          &perm_sorted, true));
+        // cfg.reserved[6] (sort_variant): 0 = one-sweep sort (all-pass histogram + decoupled look-back, one kernel per
+        // pass), 1 = the earlier three-kernels-per-pass form (A/B); both are the same stable sort
+        if (ctx->cfg.reserved[6] == 1)
+            NB_CHECK(nbprim::radix_sort_pairs(ctx, b.key_hi, b.perm, b.key_hi_alt, b.perm_alt, n, 63, b.hist, &hi_sorted,
+                                              &perm_sorted, true));
+        else
+            NB_CHECK(nbprim::onesweep_sort_pairs(ctx, b.key_hi, b.perm, b.key_hi_alt, b.perm_alt, n, 63, b.hist, &hi_sorted,
+                                                 &perm_sorted, true));
         fix_ties_kernel<<<g256, 256, 0, ctx->stream>>>(hi_sorted, ctx->x, ctx->y, ctx->z, b.aabb_dev, perm_sorted, n,
                                                        b.dev_flags);
         NB_LAUNCH_CHECK(ctx);

@@ -1,5 +1,6 @@
 // Hand-written device primitives used by the Barnes-Hut build: exclusive prefix sum over uint32 and a stable
-// LSD radix sort of (uint64 key, uint32 value) pairs.  Replaces the reference's serial single_task scan
+// LSD radix sort of (uint64 key, uint32 value) pairs (one-sweep form with decoupled look-back, plus the earlier
+// histogram / scan / scatter form kept for A/B runs).  Replaces the reference's serial single_task scan
 // (ParallelOctreeTopDownSubtrees.cpp:461-474), its O(S^2) prefix (:491-500) and the linear-search scatter (:512-532).
 #pragma once
 #include "common.cuh"
@@ -249,6 +250,226 @@ inline int radix_sort_pairs(nb_ctx *ctx, uint64_t *keys_a, uint32_t *vals_a, uin
             rs_scatter_kernel<false><<<tiles, RS_THREADS, 0, ctx->stream>>>(kin, vin, n, shift, tiles, hist, kout, vout);
         NB_LAUNCH_CHECK(ctx);
         first = false;
+        uint64_t *tk = kin; kin = kout; kout = tk;
+        uint32_t *tv = vin; vin = vout; vout = tv;
+    }
+    *keys_sorted = kin;
+    *vals_sorted = vin;
+    return NB_OK;
+}
+
+
+// ---------------------------------------------------------------------------------------------------------------
+// One-sweep form of the same stable LSD sort (default).  The digit histograms of ALL passes are taken in one read of
+// the keys before the first pass (a stable sort does not change them), so a pass is a single kernel: every tile
+// ranks its keys, publishes its per-digit counts and obtains the counts of the tiles before it by decoupled
+// look-back over a status table ({flag, count} packed in one 32-bit word per (tile, digit): 1 = the tile's own
+// count, 2 = inclusive prefix over tiles 0..t).  Tiles are numbered by an atomic ticket, so a tile only ever waits
+// for tiles that are already running.  Per pass this drops the per-tile histogram kernel (one more read of the
+// keys) and the three-kernel scan of the 256 x tiles table; the result is the same permutation bit for bit.
+// ---------------------------------------------------------------------------------------------------------------
+constexpr int OS_MAX_PASSES = 8;
+constexpr uint32_t OS_FLAG_COUNT = 1u << 30, OS_FLAG_PREFIX = 2u << 30, OS_VALUE_MASK = (1u << 30) - 1u;
+
+// all-pass digit histograms; adjacent equal digits inside a warp are added as one run (the keys of the high passes are
+// nearly sorted from the previous step, so a warp usually holds one or two distinct high digits)
+__global__ void __launch_bounds__(256)
+os_hist_kernel(const uint64_t *__restrict__ keys, uint64_t n, int passes, uint32_t *__restrict__ ghist /* [passes][256] */) {
+    __shared__ uint32_t h[OS_MAX_PASSES][RS_BINS];
+    for (int b = threadIdx.x; b < OS_MAX_PASSES * RS_BINS; b += blockDim.x) (&h[0][0])[b] = 0;
+    __syncthreads();
+    const int lane = threadIdx.x & 31;
+    const uint64_t stride = (uint64_t) gridDim.x * blockDim.x;
+    const uint64_t n_round = (n + 31) & ~31ull;   // whole warps stay in the loop together
+    for (uint64_t i = (uint64_t) blockIdx.x * blockDim.x + threadIdx.x; i < n_round; i += stride) {
+        const bool valid = i < n;
+        const uint64_t key = valid ? keys[i] : 0;
+        for (int p = 0; p < passes; ++p) {
+            const uint32_t d = valid ? (uint32_t) ((key >> (8 * p)) & 0xff) : 0x100u;
+            const uint32_t prev = __shfl_up_sync(0xffffffffu, d, 1);
+            const bool head = lane == 0 || d != prev;
+            const uint32_t heads = __ballot_sync(0xffffffffu, head);
+            if (head && valid) {
+                const uint32_t later = lane == 31 ? 0u : (heads >> (lane + 1));
+                const uint32_t run = later ? (uint32_t) __ffs(later) : (uint32_t) (32 - lane);
+                atomicAdd(&h[p][d], run);
+            }
+        }
+    }
+    __syncthreads();
+    for (int b = threadIdx.x; b < passes * RS_BINS; b += blockDim.x) {
+        const uint32_t c = (&h[0][0])[b];
+        if (c) atomicAdd(&ghist[b], c);
+    }
+}
+
+// ghist[p][d] -> exclusive prefix over d (the global start of digit d in pass p); one block, thread d owns digit d
+__global__ void __launch_bounds__(RS_BINS)
+os_scan_kernel(uint32_t *__restrict__ ghist, int passes) {
+    __shared__ uint32_t sm[RS_BINS / 32 + 1];
+    for (int p = 0; p < passes; ++p) {
+        const uint32_t v = ghist[p * RS_BINS + threadIdx.x];
+        uint32_t tot;
+        const uint32_t ex = block_excl_scan<RS_BINS>(v, &tot, sm);
+        ghist[p * RS_BINS + threadIdx.x] = ex;
+    }
+}
+
+template <int ITEMS, bool IOTA_VALS>
+__global__ void __launch_bounds__(RS_THREADS, 5)
+os_scatter_kernel(const uint64_t *__restrict__ keys_in, const uint32_t *__restrict__ vals_in, uint64_t n, int shift,
+                  const uint32_t *__restrict__ gstart /* [256] of this pass */, uint32_t *status /* [tiles][256] */,
+                  uint32_t *ticket, uint64_t *__restrict__ keys_out, uint32_t *__restrict__ vals_out) {
+    constexpr int TILE = RS_THREADS * ITEMS;
+    extern __shared__ __align__(16) unsigned char os_smem[];
+    uint64_t *skey = reinterpret_cast<uint64_t *>(os_smem);                       // TILE keys staged in digit order
+    uint32_t *sval = reinterpret_cast<uint32_t *>(skey + TILE);                   // TILE values
+    uint32_t(*cnt)[RS_BINS] = reinterpret_cast<uint32_t(*)[RS_BINS]>(sval + TILE);  // [RS_WARPS][RS_BINS]
+    uint32_t *gbase = &cnt[0][0] + RS_WARPS * RS_BINS;                            // [RS_BINS]
+    uint32_t *wsum = gbase + RS_BINS;                                             // [RS_WARPS + 1]
+    uint32_t *s_tile = wsum + RS_WARPS + 1;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (threadIdx.x == 0) *s_tile = atomicAdd(ticket, 1u);
+    for (int b = threadIdx.x; b < RS_WARPS * RS_BINS; b += RS_THREADS) (&cnt[0][0])[b] = 0;
+    __syncthreads();
+    const uint32_t tile = *s_tile;
+
+    // warp w owns the contiguous sub-tile [w*32*ITEMS, (w+1)*32*ITEMS), processed in ITEMS rounds of 32 (stable order)
+    const uint64_t tile_base = (uint64_t) tile * TILE;
+    const uint64_t wbase = tile_base + (uint64_t) warp * (32 * ITEMS);
+    uint64_t key[ITEMS];
+    uint32_t rank[ITEMS], prior_of[ITEMS];
+    const uint32_t lt = (1u << lane) - 1u;
+#pragma unroll
+    for (int k = 0; k < ITEMS; ++k) {
+        const uint64_t i = wbase + (uint64_t) k * 32 + lane;
+        key[k] = i < n ? keys_in[i] : ~0ull;
+    }
+    // rank of a key among the keys of its warp with the same digit: the leader of each group of equal digits adds the
+    // group size to the warp's counter with ONE shared-memory atomic that returns the count so far.  The ITEMS atomics
+    // of a thread do not depend on each other through registers, so they pipeline; instructions of one warp reach
+    // shared memory in program order, which keeps the ranking stable.  (Measured: splitting this into separate
+    // match / atomic / shuffle loops costs registers under the 48-register budget and is 2 % slower.)
+#pragma unroll
+    for (int k = 0; k < ITEMS; ++k) {
+        const uint64_t i = wbase + (uint64_t) k * 32 + lane;
+        const bool valid = i < n;
+        const uint32_t d = valid ? (uint32_t) ((key[k] >> shift) & 0xff) : 0x100u;  // invalid lanes never match a real digit
+        const uint32_t peers = __match_any_sync(0xffffffffu, d);
+        const int leader = __ffs(peers) - 1;
+        uint32_t prior = 0;
+        if (valid && lane == leader) prior = atomicAdd(&cnt[warp][d], (uint32_t) __popc(peers));
+        rank[k] = (uint32_t) __popc(peers & lt) | ((uint32_t) leader << 16);
+        prior_of[k] = prior;   // shuffled to the group in the second loop so the atomics issue back to back
+    }
+#pragma unroll
+    for (int k = 0; k < ITEMS; ++k) {
+        const uint32_t prior = __shfl_sync(0xffffffffu, prior_of[k], (int) (rank[k] >> 16));
+        rank[k] = prior + (rank[k] & 0xffffu);
+    }
+    __syncthreads();
+    // thread b owns digit b: exclusive prefix of the digit over the warps of the tile
+    const int b = threadIdx.x;
+    uint32_t digit_total = 0;
+#pragma unroll
+    for (int w = 0; w < RS_WARPS; ++w) {
+        const uint32_t c = cnt[w][b];
+        cnt[w][b] = digit_total;
+        digit_total += c;
+    }
+    // publish this tile's count first, so the tiles behind it can look through it while it is still looking back
+    uint32_t *my_status = status + (size_t) tile * RS_BINS + b;
+    __stcg(my_status, (tile == 0 ? OS_FLAG_PREFIX : OS_FLAG_COUNT) | digit_total);
+    uint32_t tile_total;
+    const uint32_t digit_start = block_excl_scan<RS_THREADS>(digit_total, &tile_total, wsum);
+#pragma unroll
+    for (int w = 0; w < RS_WARPS; ++w) cnt[w][b] += digit_start;
+    // decoupled look-back: bodies of digit b in the tiles before this one, four status words in flight at a time
+    uint32_t before = 0;
+    if (tile > 0) {
+        uint32_t t = tile;
+        bool done = false;
+        while (!done) {
+            uint32_t w[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+                w[j] = t > (uint32_t) j ? *(const volatile uint32_t *) (status + (size_t) (t - 1 - j) * RS_BINS + b) : OS_FLAG_PREFIX;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                if (!done) {
+                    while ((w[j] & ~OS_VALUE_MASK) == 0) w[j] = *(const volatile uint32_t *) (status + (size_t) (t - 1 - j) * RS_BINS + b);
+                    before += w[j] & OS_VALUE_MASK;
+                    if (w[j] & OS_FLAG_PREFIX) done = true;
+                }
+            }
+            t = t > 4 ? t - 4 : 0;
+        }
+        __stcg(my_status, OS_FLAG_PREFIX | (before + digit_total));
+    }
+    gbase[b] = gstart[b] + before - digit_start;
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < ITEMS; ++k) {
+        const uint64_t i = wbase + (uint64_t) k * 32 + lane;
+        if (i < n) {
+            const uint32_t d = (uint32_t) ((key[k] >> shift) & 0xff);
+            const uint32_t pos = cnt[warp][d] + rank[k];
+            skey[pos] = key[k];
+            sval[pos] = IOTA_VALS ? (uint32_t) i : vals_in[i];
+        }
+    }
+    __syncthreads();
+    const uint32_t tile_count = (uint32_t) (n - tile_base < (uint64_t) TILE ? n - tile_base : (uint64_t) TILE);
+    for (uint32_t pos = threadIdx.x; pos < tile_count; pos += RS_THREADS) {
+        const uint64_t kk = skey[pos];
+        const uint32_t d = (uint32_t) ((kk >> shift) & 0xff);
+        const uint64_t g = (uint64_t) gbase[d] + pos;
+        keys_out[g] = kk;
+        vals_out[g] = sval[pos];
+    }
+}
+
+constexpr int OS_ITEMS = 8;
+inline uint32_t os_tiles_for(uint64_t n) { return (uint32_t) ((n + RS_THREADS * OS_ITEMS - 1) / (RS_THREADS * OS_ITEMS)); }
+// scratch in uint32 elements: [passes][256] histograms, 64 words of tickets, one status table per pass
+inline size_t os_scratch_elems(uint64_t n) {
+    return (size_t) OS_MAX_PASSES * RS_BINS + 64 + (size_t) OS_MAX_PASSES * os_tiles_for(n) * RS_BINS;
+}
+constexpr size_t os_smem_bytes(int items) {
+    return (size_t) RS_THREADS * items * 12 + (size_t) (RS_WARPS * RS_BINS + RS_BINS + RS_WARPS + 1 + 3) * 4;
+}
+
+// same contract as radix_sort_pairs
+inline int onesweep_sort_pairs(nb_ctx *ctx, uint64_t *keys_a, uint32_t *vals_a, uint64_t *keys_b, uint32_t *vals_b,
+                               uint64_t n, int key_bits, uint32_t *scratch, uint64_t **keys_sorted,
+                               uint32_t **vals_sorted, bool iota_first) {
+    uint64_t *kin = keys_a, *kout = keys_b;
+    uint32_t *vin = vals_a, *vout = vals_b;
+    if (n == 0) { *keys_sorted = kin; *vals_sorted = vin; return NB_OK; }
+    const int passes = (key_bits + 7) / 8;
+    if (passes > OS_MAX_PASSES) return nb_fail(ctx, NB_ERR_INVALID, "onesweep_sort_pairs: more than 64 key bits");
+    const uint32_t tiles = os_tiles_for(n);
+    uint32_t *ghist = scratch;
+    uint32_t *tickets = scratch + (size_t) OS_MAX_PASSES * RS_BINS;
+    uint32_t *status = tickets + 64;
+    NB_CUDA(ctx, cudaMemsetAsync(scratch, 0, ((size_t) OS_MAX_PASSES * RS_BINS + 64 + (size_t) passes * tiles * RS_BINS) * sizeof(uint32_t),
+                                 ctx->stream));
+    const unsigned hgrid = (unsigned) std::min<uint64_t>((n + 2047) / 2048, (uint64_t) ctx->sm_count * 8);
+    os_hist_kernel<<<hgrid, 256, 0, ctx->stream>>>(kin, n, passes, ghist);
+    NB_LAUNCH_CHECK(ctx);
+    os_scan_kernel<<<1, RS_BINS, 0, ctx->stream>>>(ghist, passes);
+    NB_LAUNCH_CHECK(ctx);
+    constexpr size_t smem = os_smem_bytes(OS_ITEMS);
+    static_assert(smem <= 48 * 1024, "one-sweep tile must fit the default shared-memory window");
+    for (int p = 0; p < passes; ++p) {
+        uint32_t *st = status + (size_t) p * tiles * RS_BINS;
+        if (p == 0 && iota_first)
+            os_scatter_kernel<OS_ITEMS, true><<<tiles, RS_THREADS, smem, ctx->stream>>>(kin, vin, n, 8 * p, ghist + p * RS_BINS, st,
+                                                                                     tickets + p, kout, vout);
+        else
+            os_scatter_kernel<OS_ITEMS, false><<<tiles, RS_THREADS, smem, ctx->stream>>>(kin, vin, n, 8 * p, ghist + p * RS_BINS, st,
+                                                                                      tickets + p, kout, vout);
+        NB_LAUNCH_CHECK(ctx);
         uint64_t *tk = kin; kin = kout; kout = tk;
         uint32_t *tv = vin; vin = vout; vout = tv;
     }
