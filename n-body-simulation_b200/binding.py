@@ -139,6 +139,8 @@ def default_config(**overrides):
             cfg.reserved[5] = int(v)
         elif k == "sort_variant":
             cfg.reserved[6] = int(v)
+        elif k == "com_variant":
+            cfg.reserved[7] = int(v)
         elif k == "walk_variant":
             cfg.reserved[3] = int(v)
         elif k == "naive_variant":

@@ -81,6 +81,7 @@ int nb_create(const nb_config *cfg, nb_ctx **out) {
     ctx->cfg = *cfg;
     ctx->device = cfg->device;
     ctx->sm_count = prop.multiProcessorCount;
+    ctx->coop_launch = prop.cooperativeLaunch != 0;
     ctx->device_name = prop.name;
     ctx->world = cfg->world_size > 0 ? cfg->world_size : 1;
     ctx->rank = cfg->rank;

@@ -26,6 +26,7 @@
 //   5. centre of mass level by level, deepest first (one launch per depth, no atomics): a node sums its children in
 //      octant order (deterministic, bit-identical to the reference's order).
 #include <algorithm>
+#include <cooperative_groups.h>
 
 #include "scan_sort.cuh"
 
@@ -399,18 +400,18 @@ com_leaf_kernel(uint64_t n, const uint32_t *__restrict__ flags_in, const double 
     store_node(com, msum4, leaf_node[i], __dmul_rn(px[i], m), __dmul_rn(py[i], m), __dmul_rn(pz[i], m), m);
 }
 
-__global__ void __launch_bounds__(256)
-com_level_kernel(int depth, const uint32_t *__restrict__ flags_in, const uint32_t *__restrict__ level,
-                 const uint32_t *__restrict__ list, const uint2 *__restrict__ meta, double *com, double *msum4,
-                 uint32_t *__restrict__ ctab /* optional child table for the group traversal */) {
-    // flags[2] = deepest leaf = 1 + deepest internal node: nothing to do for the levels below the tree
-    if ((uint32_t) depth >= flags_in[2] || (flags_in[0] & NB_FLAG_POOL)) return;
+// One level of the bottom-up pass: internal node = sum over its children in octant order 0..7 (BarnesHutOctree.cpp:299-317).
+// `tid` / `nthreads`: this thread's index in, and the size of, the set of threads that share the level.
+template <bool COHERENT>
+__device__ __forceinline__ void com_level(int depth, const uint32_t *__restrict__ level, const uint32_t *__restrict__ list,
+                                          const uint2 *__restrict__ meta, double *com, double *msum4,
+                                          uint32_t *__restrict__ ctab, uint32_t tid, uint32_t nthreads) {
     const uint32_t count = level[depth];
     const uint32_t *nodes = list + level[NB_LEVELS + depth];
-    for (uint32_t k = blockIdx.x * blockDim.x + threadIdx.x; k < count; k += gridDim.x * blockDim.x) {
+    for (uint32_t k = tid; k < count; k += nthreads) {
         const uint32_t p = nodes[k];
         const uint32_t end = meta[p].x;
-        // children (leaves, or depth+1 nodes finished by the previous launch), indexed by their visit rank
+        // children (leaves, or depth+1 nodes finished before this level), indexed by their visit rank
         uint32_t child[8];
 #pragma unroll
         for (int r = 0; r < 8; ++r) child[r] = NB_NONE;
@@ -431,7 +432,8 @@ com_level_kernel(int depth, const uint32_t *__restrict__ flags_in, const uint32_
             const uint32_t c = child[rank_of_octant[o]];
             if (c != NB_NONE) {  // an empty octant adds 0.0 in the reference: a no-op
                 const double2 *s2 = reinterpret_cast<const double2 *>(msum4 + 4 * (size_t) c);
-                const double2 a = s2[0], b = s2[1];
+                // COHERENT: the sums of the level below were written by other CTAs of the SAME launch; read them from L2
+                const double2 a = COHERENT ? __ldcg(s2) : s2[0], b = COHERENT ? __ldcg(s2 + 1) : s2[1];
                 cx = __dadd_rn(cx, a.x);
                 cy = __dadd_rn(cy, a.y);
                 cz = __dadd_rn(cz, b.x);
@@ -444,6 +446,33 @@ com_level_kernel(int depth, const uint32_t *__restrict__ flags_in, const uint32_
             ct[0] = make_uint4(child[0], child[1], child[2], child[3]);
             ct[1] = make_uint4(child[4], child[5], child[6], child[7]);
         }
+    }
+}
+
+// one launch per level (fallback when a cooperative launch is not possible)
+__global__ void __launch_bounds__(256)
+com_level_kernel(int depth, const uint32_t *__restrict__ flags_in, const uint32_t *__restrict__ level,
+                 const uint32_t *__restrict__ list, const uint2 *__restrict__ meta, double *com, double *msum4,
+                 uint32_t *__restrict__ ctab /* optional child table for the group traversal */) {
+    // flags[2] = deepest leaf = 1 + deepest internal node: nothing to do for the levels below the tree
+    if ((uint32_t) depth >= flags_in[2] || (flags_in[0] & NB_FLAG_POOL)) return;
+    com_level<false>(depth, level, list, meta, com, msum4, ctab, blockIdx.x * blockDim.x + threadIdx.x, gridDim.x * blockDim.x);
+}
+
+// All levels in ONE cooperative launch: the grid is resident as a whole and walks the levels from the deepest internal
+// level up to the root with a grid-wide barrier between two levels (the reference spins on per-node flags inside one
+// work-group, BarnesHutOctree.cpp:327-383).  Replaces 42 dependent launches, most of them for levels below the tree.
+__global__ void __launch_bounds__(256)
+com_levels_kernel(const uint32_t *__restrict__ flags_in, const uint32_t *__restrict__ level, const uint32_t *__restrict__ list,
+                  const uint2 *__restrict__ meta, double *com, double *msum4, uint32_t *__restrict__ ctab) {
+    if (flags_in[0] & NB_FLAG_POOL) return;   // the same decision in every CTA
+    cooperative_groups::grid_group grid = cooperative_groups::this_grid();
+    int depth = (int) flags_in[2] - 1;
+    if (depth > NB_MAX_TREE_DEPTH - 1) depth = NB_MAX_TREE_DEPTH - 1;
+    const uint32_t tid = blockIdx.x * blockDim.x + threadIdx.x, nthreads = gridDim.x * blockDim.x;
+    for (; depth >= 0; --depth) {
+        com_level<true>(depth, level, list, meta, com, msum4, ctab, tid, nthreads);
+        if (depth > 0) grid.sync();
     }
 }
 
@@ -591,10 +620,37 @@ int nbk_bh_build(nb_ctx *ctx) {
         const bool want_ctab = ctx->cfg.reserved[1] == 3;
         if (want_ctab && !b.ctab) NB_CHECK(nb_alloc(ctx, &b.ctab, 8 * b.cap_nodes));
         b.ctab_valid = want_ctab;
-        for (int depth = NB_MAX_TREE_DEPTH - 1; depth >= 0; --depth) {
-            com_level_kernel<<<level_grid, 256, 0, ctx->stream>>>(depth, b.dev_flags, b.level, b.level_list, b.meta, b.com,
-                                                                  b.msum, want_ctab ? b.ctab : nullptr);
-            NB_LAUNCH_CHECK(ctx);
+        // cfg.reserved[7] (com_variant): 0 = all levels in one cooperative launch, 1 = one launch per level (A/B, and the
+        // fallback when the device or the driver refuses the cooperative launch)
+        bool done = false;
+        if (ctx->cfg.reserved[7] != 1 && ctx->coop_launch) {
+            if (b.com_ctas_per_sm == 0) {
+                int per_sm = 0;
+                NB_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, com_levels_kernel, 256, 0));
+                b.com_ctas_per_sm = per_sm < 1 ? 1 : per_sm;
+            }
+            // no more CTAs than there are internal nodes to share (< n): small systems get a cheap barrier
+            const unsigned cgrid = (unsigned) std::min<uint64_t>(g256, (uint64_t) b.com_ctas_per_sm * ctx->sm_count);
+            const uint32_t *a_flags = b.dev_flags, *a_level = b.level, *a_list = b.level_list;
+            const uint2 *a_meta = b.meta;
+            double *a_com = b.com, *a_msum = b.msum;
+            uint32_t *a_ctab = want_ctab ? b.ctab : nullptr;
+            void *args[] = {&a_flags, &a_level, &a_list, &a_meta, &a_com, &a_msum, &a_ctab};
+            const cudaError_t e = cudaLaunchCooperativeKernel((const void *) com_levels_kernel, dim3(cgrid), dim3(256), args, 0, ctx->stream);
+            if (e == cudaSuccess) {
+                ctx->launches++;
+                done = true;
+            } else {
+                (void) cudaGetLastError();   // fall back to the per-level launches below
+                ctx->coop_launch = false;
+            }
+        }
+        if (!done) {
+            for (int depth = NB_MAX_TREE_DEPTH - 1; depth >= 0; --depth) {
+                com_level_kernel<<<level_grid, 256, 0, ctx->stream>>>(depth, b.dev_flags, b.level, b.level_list, b.meta, b.com,
+                                                                      b.msum, want_ctab ? b.ctab : nullptr);
+                NB_LAUNCH_CHECK(ctx);
+            }
         }
     }
     b.built = true;

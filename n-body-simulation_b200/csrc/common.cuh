@@ -49,6 +49,7 @@ struct nb_bh_state {
     uint32_t *visits = nullptr;                              // per-body visit counters (stats)
     unsigned long long *stat_totals = nullptr;               // {visits, accepts}
     int walk_ctas_per_sm = 0, walk_ctas_threads = 0;         // occupancy of the persistent walk (cached)
+    int com_ctas_per_sm = 0;                                 // occupancy of the cooperative centre-of-mass kernel (cached)
     // device scalars
     double *aabb_dev = nullptr;                              // 7 doubles: min xyz, max xyz, edge
     double *aabb_partial = nullptr;
@@ -66,6 +67,7 @@ struct nb_ctx {
     nb_config cfg;
     int device = 0;
     int sm_count = NB_SM_COUNT_FALLBACK;
+    bool coop_launch = false;   // device supports cooperative launches (grid-wide barrier in the centre-of-mass pass)
     cudaStream_t stream = nullptr;
     std::string last_error;
     std::string device_name;

@@ -279,20 +279,31 @@ os_hist_kernel(const uint64_t *__restrict__ keys, uint64_t n, int passes, uint32
     for (int b = threadIdx.x; b < OS_MAX_PASSES * RS_BINS; b += blockDim.x) (&h[0][0])[b] = 0;
     __syncthreads();
     const int lane = threadIdx.x & 31;
+    constexpr int U = 4;                                                  // keys in flight per thread
     const uint64_t stride = (uint64_t) gridDim.x * blockDim.x;
-    const uint64_t n_round = (n + 31) & ~31ull;   // whole warps stay in the loop together
-    for (uint64_t i = (uint64_t) blockIdx.x * blockDim.x + threadIdx.x; i < n_round; i += stride) {
-        const bool valid = i < n;
-        const uint64_t key = valid ? keys[i] : 0;
-        for (int p = 0; p < passes; ++p) {
-            const uint32_t d = valid ? (uint32_t) ((key >> (8 * p)) & 0xff) : 0x100u;
-            const uint32_t prev = __shfl_up_sync(0xffffffffu, d, 1);
-            const bool head = lane == 0 || d != prev;
-            const uint32_t heads = __ballot_sync(0xffffffffu, head);
-            if (head && valid) {
-                const uint32_t later = lane == 31 ? 0u : (heads >> (lane + 1));
-                const uint32_t run = later ? (uint32_t) __ffs(later) : (uint32_t) (32 - lane);
-                atomicAdd(&h[p][d], run);
+    const uint64_t n_round = (n + 31) & ~31ull;                           // whole warps stay in the loop together
+    for (uint64_t i0 = (uint64_t) blockIdx.x * blockDim.x + threadIdx.x; i0 < n_round; i0 += U * stride) {
+        uint64_t key[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const uint64_t i = i0 + (uint64_t) u * stride;
+            key[u] = i < n ? keys[i] : 0;
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const uint64_t i = i0 + (uint64_t) u * stride;
+            if (i >= n_round) break;                                      // warp-uniform
+            const bool valid = i < n;
+            for (int p = 0; p < passes; ++p) {
+                const uint32_t d = valid ? (uint32_t) ((key[u] >> (8 * p)) & 0xff) : 0x100u;
+                const uint32_t prev = __shfl_up_sync(0xffffffffu, d, 1);
+                const bool head = lane == 0 || d != prev;
+                const uint32_t heads = __ballot_sync(0xffffffffu, head);
+                if (head && valid) {
+                    const uint32_t later = lane == 31 ? 0u : (heads >> (lane + 1));
+                    const uint32_t run = later ? (uint32_t) __ffs(later) : (uint32_t) (32 - lane);
+                    atomicAdd(&h[p][d], run);
+                }
             }
         }
     }
