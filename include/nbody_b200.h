@@ -108,6 +108,10 @@ int nb_bh_build(nb_ctx *ctx);
 /* BarnesHutAlgorithm::computeAccelerations (BarnesHutAlgorithm.hpp:43-46, .cpp:280-401), theta criterion
  * edge*rsqrt(d^2) < theta OR body leaf; requires nb_bh_build on the current positions.                    */
 int nb_bh_accel(nb_ctx *ctx);
+/* The same traversal for the bodies in storage slots [slot_begin, slot_end) only (storage order is the sorted
+ * Morton / DFS order after nb_bh_build) and without the all-gather: what one rank of a world_size-P run executes
+ * for its slice (nb_slice_bounds), callable on a single GPU -- used to profile a rank's share.               */
+int nb_bh_accel_range(nb_ctx *ctx, uint64_t slot_begin, uint64_t slot_end);
 
 /* ---- integrator ------------------------------------------------------------------------------------------ */
 /* Leapfrog part 1 (NaiveAlgorithm.cpp:140-164 = BarnesHutAlgorithm.cpp:157-182): v += a*(dt/2); x += v*dt. */

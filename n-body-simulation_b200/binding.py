@@ -46,7 +46,7 @@ EXPORTED_SYMBOLS = [
     "nb_config_default", "nb_abi_version", "nb_status_string", "nb_create", "nb_destroy", "nb_last_error",
     "nb_synchronize", "nb_device_name", "nb_set_theta", "nb_set_block_size", "nb_set_sort_bodies",
     "nb_set_precise_rsqrt", "nb_set_bodies", "nb_set_positions", "nb_num_bodies", "nb_naive_accel", "nb_bh_build",
-    "nb_bh_accel", "nb_leapfrog_part1", "nb_leapfrog_part2", "nb_leapfrog_part2_part1", "nb_advance", "nb_energy",
+    "nb_bh_accel", "nb_bh_accel_range", "nb_leapfrog_part1", "nb_leapfrog_part2", "nb_leapfrog_part2_part1", "nb_advance", "nb_energy",
     "nb_get_positions", "nb_get_velocities", "nb_get_accelerations", "nb_get_acceleration_norms",
     "nb_op_naive_accelerations", "nb_op_barnes_hut_accelerations", "nb_bh_tree_info", "nb_bh_aabb",
     "nb_bh_export_canonical", "nb_bh_sorted_bodies", "nb_bh_enable_stats", "nb_bh_get_stats",
@@ -91,6 +91,7 @@ def load_library():
     L.nb_num_bodies.restype = C.c_uint64
     for f in ("nb_naive_accel", "nb_bh_build", "nb_bh_accel"):
         getattr(L, f).argtypes = [vp]
+    L.nb_bh_accel_range.argtypes = [vp, C.c_uint64, C.c_uint64]
     for f in ("nb_leapfrog_part1", "nb_leapfrog_part2", "nb_leapfrog_part2_part1"):
         getattr(L, f).argtypes = [vp, C.c_double]
     L.nb_advance.argtypes = [vp, C.c_int, C.c_double, C.c_uint32, _dp]
@@ -262,6 +263,9 @@ class Context:
 
     def bh_accel(self):
         self._ck(self.L.nb_bh_accel(self.h))
+
+    def bh_accel_range(self, begin, end):
+        self._ck(self.L.nb_bh_accel_range(self.h, C.c_uint64(begin), C.c_uint64(end)))
 
     def leapfrog_part1(self, dt):
         self._ck(self.L.nb_leapfrog_part1(self.h, dt))

@@ -255,6 +255,14 @@ int nb_bh_accel(nb_ctx *ctx) {
     return NB_OK;
 }
 
+int nb_bh_accel_range(nb_ctx *ctx, uint64_t slot_begin, uint64_t slot_end) {
+    if (!ctx || !ctx->n) return nb_fail(ctx, NB_ERR_INVALID, "nb_bh_accel_range: no bodies");
+    if (slot_begin > slot_end || slot_end > ctx->n) return nb_fail(ctx, NB_ERR_INVALID, "nb_bh_accel_range: bad slot range");
+    NB_CUDA(ctx, cudaSetDevice(ctx->device));
+    nb_timer_scope t(ctx, NB_T_ACCEL);
+    return nbk_bh_accel(ctx, slot_begin, slot_end);
+}
+
 int nb_leapfrog_part1(nb_ctx *ctx, double dt) {
     if (!ctx) return NB_ERR_INVALID;
     NB_CUDA(ctx, cudaSetDevice(ctx->device));

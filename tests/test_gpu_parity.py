@@ -382,6 +382,28 @@ def test_sort_forms_give_the_same_order(nb, oracle, n, gen):
         assert np.array_equal(got[0][0], oracle.Tree(m, px, py, pz).sorted_bodies)
 
 
+@pytest.mark.parametrize("n,world", [(5000, 3), (600001, 8), (1 << 21, 2)])
+def test_bh_slices_assemble_to_the_full_traversal(nb, n, world):
+    """nb_bh_accel_range evaluates the storage slots one rank of a world_size-P run owns (nb_slice_bounds); the slices of
+    all ranks, evaluated one after the other on one GPU, give exactly the accelerations of the full traversal."""
+    m, x, y, z, *_ = nb.generators.uniform_sphere(n, seed=29)
+    c = nb.Context(device=0, theta=0.5)
+    c.set_bodies(m, x, y, z)
+    c.bh_build(); c.bh_accel()
+    want = np.stack(c.accelerations())
+    c.bh_build()
+    covered = 0
+    for r in reversed(range(world)):
+        b, e = nb.slice_bounds(n, world, r)
+        c.bh_accel_range(b, e)
+        covered += e - b
+    assert covered == n
+    assert np.array_equal(np.stack(c.accelerations()), want)
+    with pytest.raises(nb.NBodyError):
+        c.bh_accel_range(5, n + 1)
+    c.close()
+
+
 @pytest.mark.parametrize("variant", [0, 3])
 def test_bh_massless_bodies_are_invisible(nb, oracle, variant):
     """The reference skips nodes with SUM_MASSES == 0 (BarnesHutAlgorithm.cpp:349): massless bodies exert no force and
