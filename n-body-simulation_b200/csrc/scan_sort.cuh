@@ -326,22 +326,24 @@ os_scan_kernel(uint32_t *__restrict__ ghist, int passes) {
     }
 }
 
-template <int ITEMS, bool IOTA_VALS>
-__global__ void __launch_bounds__(RS_THREADS, 5)
+template <int THREADS, int ITEMS, bool IOTA_VALS>
+__global__ void __launch_bounds__(THREADS, THREADS == 256 ? 5 : 4)
 os_scatter_kernel(const uint64_t *__restrict__ keys_in, const uint32_t *__restrict__ vals_in, uint64_t n, int shift,
                   const uint32_t *__restrict__ gstart /* [256] of this pass */, uint32_t *status /* [tiles][256] */,
                   uint32_t *ticket, uint64_t *__restrict__ keys_out, uint32_t *__restrict__ vals_out) {
-    constexpr int TILE = RS_THREADS * ITEMS;
+    constexpr int TILE = THREADS * ITEMS;
+    constexpr int WARPS = THREADS / 32;
+    static_assert(THREADS >= RS_BINS, "thread b owns digit b");
     extern __shared__ __align__(16) unsigned char os_smem[];
     uint64_t *skey = reinterpret_cast<uint64_t *>(os_smem);                       // TILE keys staged in digit order
     uint32_t *sval = reinterpret_cast<uint32_t *>(skey + TILE);                   // TILE values
-    uint32_t(*cnt)[RS_BINS] = reinterpret_cast<uint32_t(*)[RS_BINS]>(sval + TILE);  // [RS_WARPS][RS_BINS]
-    uint32_t *gbase = &cnt[0][0] + RS_WARPS * RS_BINS;                            // [RS_BINS]
-    uint32_t *wsum = gbase + RS_BINS;                                             // [RS_WARPS + 1]
-    uint32_t *s_tile = wsum + RS_WARPS + 1;
+    uint32_t(*cnt)[RS_BINS] = reinterpret_cast<uint32_t(*)[RS_BINS]>(sval + TILE);  // [WARPS][RS_BINS]
+    uint32_t *gbase = &cnt[0][0] + WARPS * RS_BINS;                            // [RS_BINS]
+    uint32_t *wsum = gbase + RS_BINS;                                             // [WARPS + 1]
+    uint32_t *s_tile = wsum + WARPS + 1;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     if (threadIdx.x == 0) *s_tile = atomicAdd(ticket, 1u);
-    for (int b = threadIdx.x; b < RS_WARPS * RS_BINS; b += RS_THREADS) (&cnt[0][0])[b] = 0;
+    for (int b = threadIdx.x; b < WARPS * RS_BINS; b += THREADS) (&cnt[0][0])[b] = 0;
     __syncthreads();
     const uint32_t tile = *s_tile;
 
@@ -381,23 +383,28 @@ os_scatter_kernel(const uint64_t *__restrict__ keys_in, const uint32_t *__restri
     __syncthreads();
     // thread b owns digit b: exclusive prefix of the digit over the warps of the tile
     const int b = threadIdx.x;
+    const bool owner = THREADS == RS_BINS || b < RS_BINS;
     uint32_t digit_total = 0;
+    if (owner) {
 #pragma unroll
-    for (int w = 0; w < RS_WARPS; ++w) {
-        const uint32_t c = cnt[w][b];
-        cnt[w][b] = digit_total;
-        digit_total += c;
+        for (int w = 0; w < WARPS; ++w) {
+            const uint32_t c = cnt[w][b];
+            cnt[w][b] = digit_total;
+            digit_total += c;
+        }
     }
     // publish this tile's count first, so the tiles behind it can look through it while it is still looking back
     uint32_t *my_status = status + (size_t) tile * RS_BINS + b;
-    __stcg(my_status, (tile == 0 ? OS_FLAG_PREFIX : OS_FLAG_COUNT) | digit_total);
+    if (owner) __stcg(my_status, (tile == 0 ? OS_FLAG_PREFIX : OS_FLAG_COUNT) | digit_total);
     uint32_t tile_total;
-    const uint32_t digit_start = block_excl_scan<RS_THREADS>(digit_total, &tile_total, wsum);
+    const uint32_t digit_start = block_excl_scan<THREADS>(digit_total, &tile_total, wsum);
+    if (owner) {
 #pragma unroll
-    for (int w = 0; w < RS_WARPS; ++w) cnt[w][b] += digit_start;
+        for (int w = 0; w < WARPS; ++w) cnt[w][b] += digit_start;
+    }
     // decoupled look-back: bodies of digit b in the tiles before this one, four status words in flight at a time
     uint32_t before = 0;
-    if (tile > 0) {
+    if (owner && tile > 0) {
         uint32_t t = tile;
         bool done = false;
         while (!done) {
@@ -417,7 +424,7 @@ os_scatter_kernel(const uint64_t *__restrict__ keys_in, const uint32_t *__restri
         }
         __stcg(my_status, OS_FLAG_PREFIX | (before + digit_total));
     }
-    gbase[b] = gstart[b] + before - digit_start;
+    if (owner) gbase[b] = gstart[b] + before - digit_start;
     __syncthreads();
 #pragma unroll
     for (int k = 0; k < ITEMS; ++k) {
@@ -431,7 +438,7 @@ os_scatter_kernel(const uint64_t *__restrict__ keys_in, const uint32_t *__restri
     }
     __syncthreads();
     const uint32_t tile_count = (uint32_t) (n - tile_base < (uint64_t) TILE ? n - tile_base : (uint64_t) TILE);
-    for (uint32_t pos = threadIdx.x; pos < tile_count; pos += RS_THREADS) {
+    for (uint32_t pos = threadIdx.x; pos < tile_count; pos += THREADS) {
         const uint64_t kk = skey[pos];
         const uint32_t d = (uint32_t) ((kk >> shift) & 0xff);
         const uint64_t g = (uint64_t) gbase[d] + pos;
@@ -440,14 +447,21 @@ os_scatter_kernel(const uint64_t *__restrict__ keys_in, const uint32_t *__restri
     }
 }
 
-constexpr int OS_ITEMS = 8;
-inline uint32_t os_tiles_for(uint64_t n) { return (uint32_t) ((n + RS_THREADS * OS_ITEMS - 1) / (RS_THREADS * OS_ITEMS)); }
+// tile geometry: OS_THREADS x OS_ITEMS keys per tile
+#ifndef NB_OS_THREADS
+#define NB_OS_THREADS 256
+#endif
+#ifndef NB_OS_ITEMS
+#define NB_OS_ITEMS 8
+#endif
+constexpr int OS_THREADS = NB_OS_THREADS, OS_ITEMS = NB_OS_ITEMS;
+inline uint32_t os_tiles_for(uint64_t n) { return (uint32_t) ((n + OS_THREADS * OS_ITEMS - 1) / (OS_THREADS * OS_ITEMS)); }
 // scratch in uint32 elements: [passes][256] histograms, 64 words of tickets, one status table per pass
 inline size_t os_scratch_elems(uint64_t n) {
     return (size_t) OS_MAX_PASSES * RS_BINS + 64 + (size_t) OS_MAX_PASSES * os_tiles_for(n) * RS_BINS;
 }
-constexpr size_t os_smem_bytes(int items) {
-    return (size_t) RS_THREADS * items * 12 + (size_t) (RS_WARPS * RS_BINS + RS_BINS + RS_WARPS + 1 + 3) * 4;
+constexpr size_t os_smem_bytes(int threads, int items) {
+    return (size_t) threads * items * 12 + (size_t) ((threads / 32) * RS_BINS + RS_BINS + threads / 32 + 1 + 3) * 4;
 }
 
 // same contract as radix_sort_pairs
@@ -470,16 +484,16 @@ inline int onesweep_sort_pairs(nb_ctx *ctx, uint64_t *keys_a, uint32_t *vals_a, 
     NB_LAUNCH_CHECK(ctx);
     os_scan_kernel<<<1, RS_BINS, 0, ctx->stream>>>(ghist, passes);
     NB_LAUNCH_CHECK(ctx);
-    constexpr size_t smem = os_smem_bytes(OS_ITEMS);
+    constexpr size_t smem = os_smem_bytes(OS_THREADS, OS_ITEMS);
     static_assert(smem <= 48 * 1024, "one-sweep tile must fit the default shared-memory window");
     for (int p = 0; p < passes; ++p) {
         uint32_t *st = status + (size_t) p * tiles * RS_BINS;
         if (p == 0 && iota_first)
-            os_scatter_kernel<OS_ITEMS, true><<<tiles, RS_THREADS, smem, ctx->stream>>>(kin, vin, n, 8 * p, ghist + p * RS_BINS, st,
-                                                                                     tickets + p, kout, vout);
+            os_scatter_kernel<OS_THREADS, OS_ITEMS, true><<<tiles, OS_THREADS, smem, ctx->stream>>>(kin, vin, n, 8 * p, ghist + p * RS_BINS, st,
+                                                                                                 tickets + p, kout, vout);
         else
-            os_scatter_kernel<OS_ITEMS, false><<<tiles, RS_THREADS, smem, ctx->stream>>>(kin, vin, n, 8 * p, ghist + p * RS_BINS, st,
-                                                                                      tickets + p, kout, vout);
+            os_scatter_kernel<OS_THREADS, OS_ITEMS, false><<<tiles, OS_THREADS, smem, ctx->stream>>>(kin, vin, n, 8 * p, ghist + p * RS_BINS, st,
+                                                                                                  tickets + p, kout, vout);
         NB_LAUNCH_CHECK(ctx);
         uint64_t *tk = kin; kin = kout; kout = tk;
         uint32_t *tv = vin; vin = vout; vout = tv;
