@@ -619,7 +619,8 @@ int nbk_bh_accel(nb_ctx *ctx, uint64_t s_begin, uint64_t s_end) {
         // 320 tiles measured 84.4 / 84.2 / 84.5), 1 = one contiguous chunk per SM (85.2 ms: L1 hit rate up, but 148
         // distant windows at a time drop the L2 hit rate from 92 % to 71 %).  A rank's slice of an 8-GPU run (2^21 bodies,
         // nb_bh_accel_range on one GPU) takes 11.25 ms for runs of 20 / 40 / 80 / 160 tiles alike, against 84.2 / 8 = 10.5:
-        // the 7 % are the tail -- a warp needs ~1 ms per tile, and 65536 tiles over 5920 resident warps is 11.07 rounds
+        // the 7 % are the tail -- a warp needs ~1 ms per tile, so the last round runs on partly empty SMs (smaller grids
+        // that make the rounds come out even are slower: 11.5 ms at exactly 12 rounds)
         if (ctx->cfg.reserved[5] == 1) NB_LAUNCH_IW(false, true, 0, pg);
         else NB_LAUNCH_IW(false, true, 160, pg);
     } else {
