@@ -20,6 +20,7 @@
 #include "common.cuh"
 
 #include <algorithm>
+#include <type_traits>
 
 #define NB_BH_MAX_LEVELS 64
 
@@ -152,6 +153,13 @@ bh_traverse_kernel(const double4 *__restrict__ com, const uint2 *__restrict__ me
 // prefetch.global.L1 of the next node (98-102 ms); ticketed one-tile-per-warp assignment on a full grid (87 ms); one
 // straight-line accept/skip decision for leaves and cells instead of the leaf branch (88.9 ms).
 // ---------------------------------------------------------------------------------------------------------------------
+// the oracle's acceptance expression (BarnesHutAlgorithm.cpp:355-359) with correctly rounded operations
+__device__ __forceinline__ bool exact_accept(double dx, double dy, double dz, double edge0, uint32_t depth, double theta) {
+    const double d2o = __dadd_rn(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)), __dmul_rn(dz, dz));
+    const double rs = __ddiv_rn(1.0, __dsqrt_rn(d2o));
+    return __dmul_rn(scale_pow2(edge0, depth), rs) < theta;
+}
+
 template <bool STATS, bool PERSIST, uint32_t RUN>
 __global__ void __launch_bounds__(256, 5)
 bh_traverse_iw_kernel(const double4 *__restrict__ com, const uint2 *__restrict__ meta, const uint32_t *__restrict__ flags,
@@ -159,11 +167,13 @@ bh_traverse_iw_kernel(const double4 *__restrict__ com, const uint2 *__restrict__
                       const double *__restrict__ sy, const double *__restrict__ sz, uint64_t s_begin, uint64_t s_end,
                       double theta, double eps2, double G, double *__restrict__ asx, double *__restrict__ asy,
                       double *__restrict__ asz, uint32_t *__restrict__ visits, unsigned long long *__restrict__ totals,
-                      uint32_t *__restrict__ tile_counters, uint32_t n_chunks) {
+                      uint32_t *__restrict__ tile_counters, uint32_t n_chunks, double k1875) {
     const double edge0 = aabb[6];
     const double ratio0 = (edge0 / theta) * (edge0 / theta);
     const bool scalable = ratio0 > 1e-200 && ratio0 < 1e200;   // theta == 0 or absurd boxes: always the exact branch
     const int W0 = __double2hiint(ratio0);
+    int W0m1 = W0 - 1;
+    asm("" : "+r"(W0m1));   // opaque: keep W_0 - 1 itself in a register, not W_0 plus an add per node
     // fast decisions need eps2 <= 2^-24 (edge_d/theta)^2 and a normal threshold: depth << 21 must stay below t_lim
     int w_min = __double2hiint(eps2) + (24 << 20);
     if (w_min < (64 << 20)) w_min = 64 << 20;
@@ -181,6 +191,12 @@ bh_traverse_iw_kernel(const double4 *__restrict__ com, const uint2 *__restrict__
     }
     uint64_t tile = ((uint64_t) blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     unsigned long long nvis_w = 0, nacc_w = 0;
+    // The depth guard "t >= t_lim" (eps2 not negligible against (edge_d/theta)^2) cannot fire when even the deepest level
+    // of THIS tree (flags[2], written by the build) is below the limit: the tile loop exists in two instantiations and
+    // the common one has no guard in the cursor step.
+    const bool guard_needed = ((flags[2] + 1u) << 21) >= t_lim || flags[2] >= 2047u;
+    auto run = [&](auto guard_tag) {
+    constexpr bool GUARD = decltype(guard_tag)::value;
     for (;;) {
         if constexpr (PERSIST) {
             bool have = false;
@@ -234,17 +250,15 @@ bh_traverse_iw_kernel(const double4 *__restrict__ com, const uint2 *__restrict__
                     next = max(mt.x, cur + 1);
                 } else {
                     const uint32_t t = mt.y << 21;                       // depth << 21 (the rank bits shift out)
-                    const int diff = __double2hiint(D) - (W0 - (int) t);
-                    bool accept = diff > 0;
-                    if (t >= t_lim || (uint32_t) (diff + 1) <= 2u) {
-                        // undecided: the oracle's exact expression, no contraction
-                        const uint32_t depth = mt.y & NB_PAYLOAD_MASK;
-                        const double d2o = __dadd_rn(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)), __dmul_rn(dz, dz));
-                        const double rs = __ddiv_rn(1.0, __dsqrt_rn(d2o));
-                        accept = __dmul_rn(scale_pow2(edge0, depth), rs) < theta;
+                    const int band = __double2hiint(D) - (W0m1 - (int) t);   // hiword(D) - W_d + 1
+                    bool accept = band > 1;                              // hiword(D) > W_d
+                    if ((GUARD && t >= t_lim) || (uint32_t) band <= 2u) {
+                        // undecided (|hiword(D) - W_d| <= 1, or a depth where eps2 matters): the oracle's exact
+                        // expression, no contraction
+                        accept = exact_accept(dx, dy, dz, edge0, mt.y & NB_PAYLOAD_MASK, theta);
                     }
                     interact = accept;
-                    next = accept ? max(mt.x, cur + 1) : cur + 1;  // skip links always point forward
+                    next = accept ? mt.x : cur + 1;  // a skip link points behind the node's subtree: always > cur
                     if (STATS) nvis += 1u;
                 }
                 if (interact) {
@@ -253,7 +267,7 @@ bh_traverse_iw_kernel(const double4 *__restrict__ com, const uint2 *__restrict__
                     const double y2 = y0 * y0;
                     const double e = fma(-D, y2, 1.0);
                     const double y3 = y2 * y0;
-                    const double p = fma(1.875, e, 1.5);
+                    const double p = fma(k1875, e, 1.5);   // 1.875 arrives as a kernel parameter: one LDC instead of two moves
                     const double q = fma(p, e, 1.0);
                     const double s = (y3 * c.w) * q;
                     ax = fma(dx, s, ax);
@@ -272,6 +286,9 @@ bh_traverse_iw_kernel(const double4 *__restrict__ com, const uint2 *__restrict__
         if (STATS) { nvis_w += nvis; nacc_w += nacc; }
         if (!PERSIST) break;
     }
+    };
+    if (guard_needed) run(std::true_type{});
+    else run(std::false_type{});
     if (STATS) {
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) {
@@ -597,7 +614,7 @@ int nbk_bh_accel(nb_ctx *ctx, uint64_t s_begin, uint64_t s_end) {
     bh_traverse_iw_kernel<ST, PERSIST, RUN><<<GRID, threads, 0, ctx->stream>>>(                                         \
         com, b.meta, b.dev_flags, ctx->n, b.aabb_dev, ctx->x, ctx->y, ctx->z, s_begin, s_end, ctx->cfg.theta,           \
         ctx->cfg.epsilon2, ctx->cfg.G, ctx->ax, ctx->ay, ctx->az, b.visits, b.stat_totals, b.dev_flags + 8,             \
-        (uint32_t) std::min<int>(ctx->sm_count, 1024))
+        (uint32_t) std::min<int>(ctx->sm_count, 1024), 1.875)
     const int wv = ctx->cfg.reserved[3];
     if (b.stats_enabled) {
         NB_CUDA(ctx, cudaMemsetAsync(b.stat_totals, 0, 8 * sizeof(unsigned long long), ctx->stream));
