@@ -135,7 +135,7 @@ bh_traverse_kernel(const double4 *__restrict__ com, const uint2 *__restrict__ me
 //     test and the force;
 //   * positive doubles order like their bit patterns, so "D > (edge_d/theta)^2" is decided by comparing HIGH WORDS:
 //     W_d = hiword((edge_0/theta)^2) - (depth << 21)  (the edge halves exactly per level); accept when
-//     hiword(D) >= W_d + 2, open when hiword(D) <= W_d - 2.  The band in between (relative width 2^-19) and every
+//     hiword(D) >= W_d + 2, open when hiword(D) <= W_d - 2 (evaluated as V = hiword(D) + (depth << 21) against W_0 +- 1).  The band in between (relative width 2^-19) and every
 //     depth for which eps2 is not negligible against (edge_d/theta)^2 take the oracle's exact expression
 //     (BarnesHutAlgorithm.cpp:355-359) with correctly rounded operations, so the decision is the reference's.  No
 //     per-depth fp64 thresholds, nothing spills under the 48-register budget (40 warps per SM);
@@ -148,6 +148,13 @@ bh_traverse_kernel(const double4 *__restrict__ com, const uint2 *__restrict__ me
 //     57 % -> 62 %, 89.6 ms -> 84.2 ms.  tile_counters: one uint32 per queue, zeroed before the launch.
 //     The queue bookkeeping must not add live values to the cursor loop: with RUN as a run-time argument ptxas spilled
 //     two loop invariants and the walk fell back to 90 ms, hence the template constant.
+//   * the cursor step is issue bound, so every instruction taken out of it shows: 1.875 of the Taylor term arrives as a
+//     kernel parameter (one LDC instead of two moves that ptxas re-materialised per node under the register budget), the
+//     acceptance test is ONE multiply-add V = hiword(D) + (depth << 21) and two compares against W_0 + 1 and W_0 - 1
+//     (kept opaque so they are not re-derived per node), the skip link is used as it is (it always points behind the
+//     node's subtree, no max), and the depth guard t >= t_lim is compiled out of the loop when the deepest level of
+//     THIS tree (flags[2]) cannot reach it.  56 -> 45 SASS instructions per accepted cell, 84.2 -> 77.2 ms at N = 2^24,
+//     bit-identical results.
 // Explored on top of this and rejected (N = 2^24, theta = 0.5, all parity-green): issuing the next node's loads before
 // the force arithmetic (software pipelining: 95 ms, the 12 extra live registers cost 20 % of the resident warps);
 // prefetch.global.L1 of the next node (98-102 ms); ticketed one-tile-per-warp assignment on a full grid (87 ms); one
@@ -172,8 +179,8 @@ bh_traverse_iw_kernel(const double4 *__restrict__ com, const uint2 *__restrict__
     const double ratio0 = (edge0 / theta) * (edge0 / theta);
     const bool scalable = ratio0 > 1e-200 && ratio0 < 1e200;   // theta == 0 or absurd boxes: always the exact branch
     const int W0 = __double2hiint(ratio0);
-    int W0m1 = W0 - 1;
-    asm("" : "+r"(W0m1));   // opaque: keep W_0 - 1 itself in a register, not W_0 plus an add per node
+    int Whi = W0 + 1, Wlo = W0 - 1;
+    asm("" : "+r"(Whi), "+r"(Wlo));   // opaque: two plain compare operands, not W_0 plus an add per node
     // fast decisions need eps2 <= 2^-24 (edge_d/theta)^2 and a normal threshold: depth << 21 must stay below t_lim
     int w_min = __double2hiint(eps2) + (24 << 20);
     if (w_min < (64 << 20)) w_min = 64 << 20;
@@ -250,9 +257,9 @@ bh_traverse_iw_kernel(const double4 *__restrict__ com, const uint2 *__restrict__
                     next = max(mt.x, cur + 1);
                 } else {
                     const uint32_t t = mt.y << 21;                       // depth << 21 (the rank bits shift out)
-                    const int band = __double2hiint(D) - (W0m1 - (int) t);   // hiword(D) - W_d + 1
-                    bool accept = band > 1;                              // hiword(D) > W_d
-                    if ((GUARD && t >= t_lim) || (uint32_t) band <= 2u) {
+                    const int V = __double2hiint(D) + (int) t;           // one multiply-add; compare with W_0 -+ 1
+                    bool accept = V > Whi;                               // hiword(D) - W_d >= 2
+                    if ((GUARD && t >= t_lim) || (!accept && V >= Wlo)) {
                         // undecided (|hiword(D) - W_d| <= 1, or a depth where eps2 matters): the oracle's exact
                         // expression, no contraction
                         accept = exact_accept(dx, dy, dz, edge0, mt.y & NB_PAYLOAD_MASK, theta);
