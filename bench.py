@@ -45,8 +45,8 @@ BH_BYTES_PER_VISIT = 40.0            # com xyz + mass (32 B) + skip/m
 BH_BYTES_PER_BODY = 48.0             # position in, acceleration out
 NAIVE_TILE = 256                     # --block_size used for the benchmark (shared-memory tile length)
 # dram__bytes_read.sum + dram__bytes_write.sum per launch from the `ncu --set full` captures summarised under profiles/
-# (naive: N = 2^20, profiles/naive_accel_r01b.txt; Barnes-Hut walk: N = 2^24, profiles/bh_traverse_r01b.txt)
-NCU_TRAFFIC_BYTES = {("naive", 1 << 20): 123.167744e6 + 55.533824e6, ("bh", 1 << 24): 2.580038e9 + 401.008896e6}
+# (naive: N = 2^20, profiles/naive_accel_r01b.txt; Barnes-Hut walk: N = 2^24, profiles/bh_traverse_r01c.txt)
+NCU_TRAFFIC_BYTES = {("naive", 1 << 20): 123.167744e6 + 55.533824e6, ("bh", 1 << 24): 2.557424e9 + 400.486656e6}
 
 
 def parse_args():
