@@ -7,7 +7,8 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-_LIB = os.path.join(_HERE, "libnbody_b200.so")
+# NB_LIB: developer override used by the A/B scripts under tools/ to time an earlier build of the library
+_LIB = os.environ.get("NB_LIB") or os.path.join(_HERE, "libnbody_b200.so")
 
 NB_COMM_ID_BYTES = 128
 NB_T_COUNT = 10
@@ -132,12 +133,10 @@ def default_config(**overrides):
     for k, v in overrides.items():
         if k == "ipt":
             cfg.reserved[0] = int(v)
-        elif k in ("single_phase_walk", "bh_variant"):
+        elif k == "unfused_advance":
             cfg.reserved[1] = int(v)
         elif k == "naive_segments":
             cfg.reserved[4] = int(v)
-        elif k == "walk_run_len":
-            cfg.reserved[5] = int(v)
         elif k == "sort_variant":
             cfg.reserved[6] = int(v)
         elif k == "com_variant":

@@ -26,6 +26,8 @@ int nb_fail(nb_ctx *ctx, int status, const char *fmt, ...) {
 
 extern "C" {
 
+static void release_state(nb_ctx *ctx);
+
 int nb_abi_version(void) { return NB_ABI_VERSION; }
 
 const char *nb_status_string(int s) {
@@ -76,7 +78,7 @@ int nb_create(const nb_config *cfg, nb_ctx **out) {
     if (cudaGetDeviceCount(&count) != cudaSuccess || count <= 0 || cfg->device >= count) return NB_ERR_NO_DEVICE;
     cudaDeviceProp prop;
     if (cudaGetDeviceProperties(&prop, cfg->device) != cudaSuccess) return NB_ERR_NO_DEVICE;
-    if (prop.major < 10) return NB_ERR_NO_DEVICE;  // kernels are compiled for sm_100a only
+    if (prop.major != 10) return NB_ERR_NO_DEVICE;  // the kernels are sm_100a cubins: they load on compute capability 10.x only
     nb_ctx *ctx = new nb_ctx();
     ctx->cfg = *cfg;
     ctx->device = cfg->device;
@@ -101,14 +103,10 @@ void nb_destroy(nb_ctx *ctx) {
     if (!ctx) return;
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
+    release_state(ctx);          // unmaps the peers' slabs first (collective, while the communicator is alive)
     nbk_comm_destroy(ctx);
     nbk_bh_release(ctx);
-    nb_free(&ctx->m); nb_free(&ctx->x); nb_free(&ctx->y); nb_free(&ctx->z);
-    nb_free(&ctx->vx); nb_free(&ctx->vy); nb_free(&ctx->vz);
-    nb_free(&ctx->ax); nb_free(&ctx->ay); nb_free(&ctx->az);
-    nb_free(&ctx->anorm); nb_free(&ctx->src); nb_free(&ctx->e_partial); nb_free(&ctx->naive_partial);
-    for (int k = 0; k < 10; ++k) nb_free(&ctx->alt[k]);
-    nb_free(&ctx->id); nb_free(&ctx->id_alt);
+    nb_free(&ctx->src); nb_free(&ctx->naive_partial); nb_free(&ctx->barrier_word);
     for (int i = 0; i < 2 * NB_T_COUNT; ++i) cudaEventDestroy(ctx->ev[i]);
     for (int i = 0; i < 8; ++i) cudaEventDestroy(ctx->user_ev[i]);
     cudaStreamDestroy(ctx->stream);
@@ -139,28 +137,36 @@ int nb_set_precise_rsqrt(nb_ctx *ctx, int p) { if (!ctx) return NB_ERR_INVALID; 
 uint64_t nb_num_bodies(const nb_ctx *ctx) { return ctx ? ctx->n : 0; }
 uint64_t nb_launch_count(const nb_ctx *ctx) { return ctx ? ctx->launches : 0; }
 
+static void release_state(nb_ctx *ctx) {
+    nbk_comm_unmap_peers(ctx);   // nobody may still address this slab when it is freed
+    if (ctx->slab) cudaFree(ctx->slab);
+    ctx->slab = nullptr;
+    ctx->slab_bytes = 0;
+    ctx->m = ctx->x = ctx->y = ctx->z = ctx->vx = ctx->vy = ctx->vz = ctx->ax = ctx->ay = ctx->az = ctx->anorm = nullptr;
+    for (int k = 0; k < 10; ++k) ctx->alt[k] = nullptr;
+    nb_free(&ctx->id); nb_free(&ctx->id_alt); nb_free(&ctx->e_partial);
+    ctx->cap = 0;
+}
+
 static int ensure_capacity(nb_ctx *ctx, uint64_t n) {
     // arrays that take part in the in-place all-gather need world * ceil(n/world) elements
     const uint64_t chunk = (n + ctx->world - 1) / ctx->world;
-    const uint64_t need = chunk * ctx->world + 32;
+    const uint64_t need = ((chunk * ctx->world + 32 + 31) / 32) * 32;   // 256-byte multiples: every array stays aligned
     if (need <= ctx->cap) return NB_OK;
     NB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-    NB_CHECK(nb_alloc(ctx, &ctx->m, need));
-    NB_CHECK(nb_alloc(ctx, &ctx->x, need));
-    NB_CHECK(nb_alloc(ctx, &ctx->y, need));
-    NB_CHECK(nb_alloc(ctx, &ctx->z, need));
-    NB_CHECK(nb_alloc(ctx, &ctx->vx, need));
-    NB_CHECK(nb_alloc(ctx, &ctx->vy, need));
-    NB_CHECK(nb_alloc(ctx, &ctx->vz, need));
-    NB_CHECK(nb_alloc(ctx, &ctx->ax, need));
-    NB_CHECK(nb_alloc(ctx, &ctx->ay, need));
-    NB_CHECK(nb_alloc(ctx, &ctx->az, need));
-    NB_CHECK(nb_alloc(ctx, &ctx->anorm, need));
-    for (int k = 0; k < 10; ++k) NB_CHECK(nb_alloc(ctx, &ctx->alt[k], need));
+    release_state(ctx);
+    ctx->slab_bytes = (size_t) 21 * need * sizeof(double);
+    NB_CUDA(ctx, cudaMalloc((void **) &ctx->slab, ctx->slab_bytes));
+    double *base = reinterpret_cast<double *>(ctx->slab);
+    double **cur[10] = {&ctx->m, &ctx->x, &ctx->y, &ctx->z, &ctx->vx, &ctx->vy, &ctx->vz, &ctx->ax, &ctx->ay, &ctx->az};
+    for (int k = 0; k < 10; ++k) { *cur[k] = base + (size_t) k * need; ctx->alt[k] = base + (size_t) (10 + k) * need; }
+    ctx->anorm = base + (size_t) 20 * need;
     NB_CHECK(nb_alloc(ctx, &ctx->id, need));
     NB_CHECK(nb_alloc(ctx, &ctx->id_alt, need));
     NB_CHECK(nb_alloc(ctx, &ctx->e_partial, 2 * need + 8 + 2048));
     ctx->cap = need;
+    // multi-GPU: let every rank address every rank's slab (collective: all ranks size their state in the same call)
+    if (ctx->world > 1 && ctx->nccl_comm) NB_CHECK(nbk_comm_map_peers(ctx));
     return NB_OK;
 }
 
@@ -184,6 +190,9 @@ int nb_set_bodies(nb_ctx *ctx, uint64_t n, const double *mass, const double *x, 
     ctx->n = n;
     ctx->bh.built = false;
     ctx->identity_order = true;  // storage order == body-id order until the next Barnes-Hut build
+    ctx->a_fresh = false;        // zeros below: in order, but not the forces of these positions
+    ctx->a_order_ok = true;
+    if (ctx->bh.dev_flags) NB_CUDA(ctx, cudaMemsetAsync(ctx->bh.dev_flags, 0, 8 * sizeof(uint32_t), ctx->stream));
     NB_CHECK(h2d(ctx, ctx->m, mass, n));
     NB_CHECK(h2d(ctx, ctx->x, x, n));
     NB_CHECK(h2d(ctx, ctx->y, y, n));
@@ -222,6 +231,7 @@ int nb_set_positions(nb_ctx *ctx, const double *x, const double *y, const double
         NB_CHECK(nbk_permute_in(ctx, 3, src, dst));
     }
     ctx->bh.built = false;
+    ctx->a_fresh = false;
     NB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     return NB_OK;
 }
@@ -230,11 +240,14 @@ int nb_set_positions(nb_ctx *ctx, const double *x, const double *y, const double
 int nb_naive_accel(nb_ctx *ctx) {
     if (!ctx || !ctx->n) return nb_fail(ctx, NB_ERR_INVALID, "nb_naive_accel: no bodies");
     NB_CUDA(ctx, cudaSetDevice(ctx->device));
-    nb_timer_scope t(ctx, NB_T_ACCEL);
     uint64_t b = 0, e = ctx->n;
     nb_slice_bounds(ctx->n, ctx->world, ctx->rank, &b, &e);
-    NB_CHECK(nbk_naive_accel(ctx, b, e));
+    {
+        nb_timer_scope t(ctx, NB_T_ACCEL);
+        NB_CHECK(nbk_naive_accel(ctx, b, e));
+    }
     NB_CHECK(nbk_comm_allgather_accel(ctx, ctx->ax, ctx->ay, ctx->az, ctx->n));
+    ctx->a_fresh = ctx->a_order_ok = true;
     return NB_OK;
 }
 
@@ -244,14 +257,32 @@ int nb_bh_build(nb_ctx *ctx) {
     return nbk_bh_build(ctx);
 }
 
+// The walk of this rank's slice with one of the epilogues of bh_traverse.cu.  Several GPUs with mapped peer slabs: the
+// kernel stores its results into every rank's arrays, bracketed by two barriers -- before it, so that no rank still
+// reads (build, integrator) what a faster rank is about to overwrite; after it, so that every rank's stores have
+// landed before anybody goes on.  Otherwise (no IPC): accelerations only, then the NCCL all-gather.
+// "Acceleration Kernel Time" is the walk alone; barriers / all-gather are "Allgather".
+static int bh_walk(nb_ctx *ctx, int epilogue, double dt) {
+    uint64_t b = 0, e = ctx->n;
+    nb_slice_bounds(ctx->n, ctx->world, ctx->rank, &b, &e);
+    const bool peers = ctx->world > 1 && ctx->p2p_ok && !ctx->bh.stats_enabled;
+    if (ctx->world > 1 && !peers && epilogue != 0)
+        return nb_fail(ctx, NB_ERR_INVALID, "fused walk on several GPUs needs mapped peer slabs");
+    if (peers) NB_CHECK(nbk_comm_barrier(ctx));
+    {
+        nb_timer_scope t(ctx, NB_T_ACCEL);
+        NB_CHECK(nbk_bh_accel_fused(ctx, b, e, epilogue, dt, peers));
+    }
+    if (peers) NB_CHECK(nbk_comm_barrier(ctx));
+    else NB_CHECK(nbk_comm_allgather_accel(ctx, ctx->ax, ctx->ay, ctx->az, ctx->n));
+    return NB_OK;
+}
+
 int nb_bh_accel(nb_ctx *ctx) {
     if (!ctx || !ctx->n) return nb_fail(ctx, NB_ERR_INVALID, "nb_bh_accel: no bodies");
     NB_CUDA(ctx, cudaSetDevice(ctx->device));
-    nb_timer_scope t(ctx, NB_T_ACCEL);
-    uint64_t b = 0, e = ctx->n;
-    nb_slice_bounds(ctx->n, ctx->world, ctx->rank, &b, &e);
-    NB_CHECK(nbk_bh_accel(ctx, b, e));
-    NB_CHECK(nbk_comm_allgather_accel(ctx, ctx->ax, ctx->ay, ctx->az, ctx->n));
+    NB_CHECK(bh_walk(ctx, 0, 0.0));
+    ctx->a_fresh = ctx->a_order_ok = true;
     return NB_OK;
 }
 
@@ -260,31 +291,52 @@ int nb_bh_accel_range(nb_ctx *ctx, uint64_t slot_begin, uint64_t slot_end) {
     if (slot_begin > slot_end || slot_end > ctx->n) return nb_fail(ctx, NB_ERR_INVALID, "nb_bh_accel_range: bad slot range");
     NB_CUDA(ctx, cudaSetDevice(ctx->device));
     nb_timer_scope t(ctx, NB_T_ACCEL);
-    return nbk_bh_accel(ctx, slot_begin, slot_end);
+    NB_CHECK(nbk_bh_accel(ctx, slot_begin, slot_end));
+    ctx->a_fresh = ctx->a_order_ok = true;   // (for the slots evaluated so far: the caller assembles the slices)
+    return NB_OK;
+}
+
+static int need_ordered_accel(nb_ctx *ctx, const char *who) {
+    if (ctx->a_order_ok) return NB_OK;
+    return nb_fail(ctx, NB_ERR_INVALID, "%s: the accelerations on the device belong to positions from before the last tree "
+                   "build and were not carried through it; evaluate the forces first", who);
 }
 
 int nb_leapfrog_part1(nb_ctx *ctx, double dt) {
     if (!ctx) return NB_ERR_INVALID;
     NB_CUDA(ctx, cudaSetDevice(ctx->device));
+    NB_CHECK(need_ordered_accel(ctx, "nb_leapfrog_part1"));
     nb_timer_scope t(ctx, NB_T_LEAPFROG1);
     ctx->bh.built = false;
+    ctx->a_fresh = false;   // the positions move on
     return nbk_leapfrog_part1(ctx, dt);
 }
 int nb_leapfrog_part2(nb_ctx *ctx, double dt) {
     if (!ctx) return NB_ERR_INVALID;
     NB_CUDA(ctx, cudaSetDevice(ctx->device));
+    NB_CHECK(need_ordered_accel(ctx, "nb_leapfrog_part2"));
     nb_timer_scope t(ctx, NB_T_LEAPFROG2);
     return nbk_leapfrog_part2(ctx, dt);
 }
 int nb_leapfrog_part2_part1(nb_ctx *ctx, double dt) {
     if (!ctx) return NB_ERR_INVALID;
     NB_CUDA(ctx, cudaSetDevice(ctx->device));
+    NB_CHECK(need_ordered_accel(ctx, "nb_leapfrog_part2_part1"));
     nb_timer_scope t(ctx, NB_T_LEAPFROG1);
     ctx->bh.built = false;
+    ctx->a_fresh = false;
     return nbk_leapfrog_part2_part1(ctx, dt);
 }
 
 // ---- nb_advance: batches of steps, inner steps replayed from a CUDA graph --------------------------------------------
+// Two forms of a batch of `nsteps` leapfrog steps (the result is the same bit for bit):
+//   unfused (naive; Barnes-Hut with the instrumented walk, or on several GPUs without IPC):
+//       part 1; forces; { part 2 + part 1 in one pass; forces } x (nsteps - 1); part 2
+//   fused (Barnes-Hut): the leapfrog half-steps ride in the epilogue of the walk (bh_traverse.cu), the state is updated
+//   in place body by body and, on several GPUs, stored into every rank's arrays by the walk itself:
+//       part 1; { build; walk + part 2 + part 1 } x (nsteps - 1); build; walk + part 2
+// On one GPU the repeated unit is captured once as a CUDA graph of TWO units (a build swaps the state arrays with
+// their ping-pong partners, so the pointer configuration has period two) and replayed.
 static void drop_step_graph(nb_ctx *ctx) {
     if (ctx->step_graph) cudaGraphExecDestroy(ctx->step_graph);
     ctx->step_graph = nullptr;
@@ -296,8 +348,19 @@ static void state_pointers(const nb_ctx *ctx, const void *p[8]) {
     p[6] = ctx->bh.perm; p[7] = ctx->src;
 }
 
-// one inner step: closing half-kick of the previous step fused with kick-drift of the next, then the forces
+static bool advance_fused(const nb_ctx *ctx, int algorithm) {
+    return algorithm == 1 && !ctx->bh.stats_enabled && (ctx->world == 1 || ctx->p2p_ok) && ctx->cfg.reserved[1] != 1;
+}
+
+// the repeated unit of a batch (see above)
 static int inner_step(nb_ctx *ctx, int algorithm, double dt) {
+    if (advance_fused(ctx, algorithm)) {
+        NB_CHECK(nb_bh_build(ctx));
+        NB_CHECK(bh_walk(ctx, 2, dt));
+        ctx->bh.built = false;   // the positions moved on
+        ctx->a_fresh = false;
+        return NB_OK;
+    }
     NB_CHECK(nb_leapfrog_part2_part1(ctx, dt));
     if (algorithm == 0) return nb_naive_accel(ctx);
     NB_CHECK(nb_bh_build(ctx));
@@ -312,14 +375,42 @@ static bool graph_matches(const nb_ctx *ctx, int algorithm, double dt) {
     return memcmp(p, ctx->graph_ptrs, sizeof p) == 0;
 }
 
-// captures two inner steps; on success the host-side state (pointer roles) is back where it started
+// host-side roles of the device buffers that a step swaps (nothing a captured kernel touches: a failed capture must
+// put them back, because none of the captured kernels has run)
+struct pointer_roles {
+    double *state[10], *alt[10];
+    uint32_t *id, *id_alt, *perm, *perm_alt;
+    uint64_t *key_hi, *key_hi_alt;
+    bool identity_order, built, coop_launch;
+};
+static void save_roles(const nb_ctx *ctx, pointer_roles &r) {
+    double *const cur[10] = {ctx->m, ctx->x, ctx->y, ctx->z, ctx->vx, ctx->vy, ctx->vz, ctx->ax, ctx->ay, ctx->az};
+    for (int k = 0; k < 10; ++k) { r.state[k] = cur[k]; r.alt[k] = ctx->alt[k]; }
+    r.id = ctx->id; r.id_alt = ctx->id_alt; r.perm = ctx->bh.perm; r.perm_alt = ctx->bh.perm_alt;
+    r.key_hi = ctx->bh.key_hi; r.key_hi_alt = ctx->bh.key_hi_alt;
+    r.identity_order = ctx->identity_order; r.built = ctx->bh.built; r.coop_launch = ctx->coop_launch;
+}
+static void restore_roles(nb_ctx *ctx, const pointer_roles &r) {
+    double **cur[10] = {&ctx->m, &ctx->x, &ctx->y, &ctx->z, &ctx->vx, &ctx->vy, &ctx->vz, &ctx->ax, &ctx->ay, &ctx->az};
+    for (int k = 0; k < 10; ++k) { *cur[k] = r.state[k]; ctx->alt[k] = r.alt[k]; }
+    ctx->id = r.id; ctx->id_alt = r.id_alt; ctx->bh.perm = r.perm; ctx->bh.perm_alt = r.perm_alt;
+    ctx->bh.key_hi = r.key_hi; ctx->bh.key_hi_alt = r.key_hi_alt;
+    ctx->identity_order = r.identity_order; ctx->bh.built = r.built; ctx->coop_launch = r.coop_launch;
+}
+
+// captures two inner steps; on success the host-side state (pointer roles) is back where it started.  Any failure
+// (a launch refused under capture, pointer roles that are not periodic over two steps, instantiation) restores the
+// roles, marks the graph unusable and returns NB_OK: the caller continues on the eager path.
 static int capture_step_graph(nb_ctx *ctx, int algorithm, double dt) {
     drop_step_graph(ctx);
     const void *before[8], *after[8];
     state_pointers(ctx, before);
+    pointer_roles saved;
+    save_roles(ctx, saved);
     const bool timers = ctx->timers_enabled;
     const uint64_t launches0 = ctx->launches;
     ctx->timers_enabled = false;   // no event records inside the graph
+    ctx->capturing = true;
     cudaGraph_t graph = nullptr;
     cudaError_t e = cudaStreamBeginCapture(ctx->stream, cudaStreamCaptureModeThreadLocal);
     int rc = NB_OK;
@@ -329,16 +420,16 @@ static int capture_step_graph(nb_ctx *ctx, int algorithm, double dt) {
         e = cudaStreamEndCapture(ctx->stream, &graph);
     }
     ctx->timers_enabled = timers;
+    ctx->capturing = false;
     ctx->graph_launches = ctx->launches - launches0;
     ctx->launches = launches0;     // nothing ran yet
     state_pointers(ctx, after);
     if (e != cudaSuccess || rc != NB_OK || !graph || memcmp(before, after, sizeof before) != 0) {
         if (graph) cudaGraphDestroy(graph);
         cudaGetLastError();
+        restore_roles(ctx, saved);
         ctx->graph_unusable = true;
-        if (memcmp(before, after, sizeof before) != 0)
-            return nb_fail(ctx, NB_ERR_CUDA, "nb_advance: state pointers are not periodic over two steps");
-        return rc != NB_OK ? rc : NB_OK;   // fall back to the eager path
+        return NB_OK;
     }
     e = cudaGraphInstantiate(&ctx->step_graph, graph, 0);
     cudaGraphDestroy(graph);
@@ -362,17 +453,24 @@ int nb_advance(nb_ctx *ctx, int algorithm, double dt, uint32_t nsteps, double *m
     if (ms) for (int i = 0; i < NB_T_COUNT; ++i) ms[i] = 0;
     if (nsteps == 0) return NB_OK;
     NB_CUDA(ctx, cudaSetDevice(ctx->device));
-    // first step, eager and timed: part 1 + forces (its closing half-kick rides with the next step's part 1)
+    const bool fused = advance_fused(ctx, algorithm);
+    // the first unit runs eagerly and timed: its phase times are the sample reported for the batch
     NB_CHECK(nb_leapfrog_part1(ctx, dt));
-    if (algorithm == 0) {
-        NB_CHECK(nb_naive_accel(ctx));
+    uint32_t rest;   // repeated units still to run
+    if (fused) {
+        rest = nsteps - 1;
+        if (rest > 0) { NB_CHECK(inner_step(ctx, algorithm, dt)); --rest; }
     } else {
-        NB_CHECK(nb_bh_build(ctx));
-        NB_CHECK(nb_bh_accel(ctx));
+        if (algorithm == 0) {
+            NB_CHECK(nb_naive_accel(ctx));
+        } else {
+            NB_CHECK(nb_bh_build(ctx));
+            NB_CHECK(nb_bh_accel(ctx));
+        }
+        rest = nsteps - 1;
     }
-    if (ms && ctx->timers_enabled) NB_CHECK(nb_get_timers(ctx, ms));
-    uint32_t rest = nsteps - 1;
-    // pairs of inner steps from the graph: one GPU, no instrumentation, and enough steps to repay the capture
+    if (ms && ctx->timers_enabled && (!fused || nsteps > 1)) NB_CHECK(nb_get_timers(ctx, ms));
+    // pairs of units from the graph: one GPU, no instrumentation, and enough steps to repay the capture
     const bool graph_ok = ctx->world == 1 && !ctx->bh.stats_enabled && !ctx->graph_unusable;
     if (graph_ok && rest >= 4) {
         if (!graph_matches(ctx, algorithm, dt)) NB_CHECK(capture_step_graph(ctx, algorithm, dt));
@@ -381,14 +479,23 @@ int nb_advance(nb_ctx *ctx, int algorithm, double dt, uint32_t nsteps, double *m
             ctx->launches += ctx->graph_launches;
             rest -= 2;
         }
-        if (algorithm == 1) ctx->bh.built = true;
     }
     const bool timers = ctx->timers_enabled;
-    ctx->timers_enabled = false;   // keep the sample of the first step
+    ctx->timers_enabled = false;   // keep the sample of the first unit
     int rc = NB_OK;
     for (; rest > 0 && rc == NB_OK; --rest) rc = inner_step(ctx, algorithm, dt);
+    ctx->timers_enabled = timers && (fused && nsteps == 1);
+    if (rc == NB_OK && fused) {   // the batch's last force evaluation carries the closing half-kick
+        rc = nb_bh_build(ctx);
+        if (rc == NB_OK) rc = bh_walk(ctx, 1, dt);
+        if (rc == NB_OK) ctx->a_fresh = ctx->a_order_ok = true;
+    }
     ctx->timers_enabled = timers;
     NB_CHECK(rc);
+    if (fused) {
+        if (ms && timers && nsteps == 1) NB_CHECK(nb_get_timers(ctx, ms));
+        return NB_OK;
+    }
     NB_CHECK(nb_leapfrog_part2(ctx, dt));
     if (ms && ctx->timers_enabled) {   // Leapfrog Part 2 of the batch's last step
         double tail[NB_T_COUNT];
@@ -461,6 +568,7 @@ int nb_get_velocities(nb_ctx *ctx, double *vx, double *vy, double *vz) {
 }
 int nb_get_accelerations(nb_ctx *ctx, double *ax, double *ay, double *az) {
     if (!ctx) return NB_ERR_INVALID;
+    NB_CHECK(need_ordered_accel(ctx, "nb_get_accelerations"));
     const double *dev[3] = {ctx->ax, ctx->ay, ctx->az};
     double *host[3] = {ax, ay, az};
     return read_back(ctx, 3, dev, host);
@@ -468,6 +576,7 @@ int nb_get_accelerations(nb_ctx *ctx, double *ax, double *ay, double *az) {
 int nb_get_acceleration_norms(nb_ctx *ctx, double *anorm) {
     if (!ctx || !ctx->n || !anorm) return nb_fail(ctx, NB_ERR_INVALID, "no bodies");
     NB_CUDA(ctx, cudaSetDevice(ctx->device));
+    NB_CHECK(need_ordered_accel(ctx, "nb_get_acceleration_norms"));
     NB_CHECK(nbk_accel_norm(ctx));
     const double *dev[1] = {ctx->anorm};
     double *host[1] = {anorm};
@@ -489,6 +598,8 @@ static int upload_for_op(nb_ctx *ctx, uint64_t n, const double *mass, const doub
     ctx->n = n;
     ctx->bh.built = false;
     ctx->identity_order = true;
+    ctx->a_fresh = false;
+    ctx->a_order_ok = true;
     NB_CHECK(h2d(ctx, ctx->m, mass, n));
     NB_CHECK(h2d(ctx, ctx->x, x, n));
     NB_CHECK(h2d(ctx, ctx->y, y, n));
@@ -562,23 +673,26 @@ int nb_measure_fp64_peak(nb_ctx *ctx, double *tflops) {
 // ---- Barnes-Hut inspection -------------------------------------------------------------------------------------------------
 static int check_bh_flags(nb_ctx *ctx) {
     nb_bh_state &b = ctx->bh;
-    if (!b.built || !b.dev_flags) return NB_OK;
-    uint32_t f[4];
+    if (!b.dev_flags) return NB_OK;
+    uint32_t f[5];
     NB_CUDA(ctx, cudaMemcpy(f, b.dev_flags, sizeof f, cudaMemcpyDeviceToHost));
-    b.num_internal = f[1];
-    b.num_nodes = ctx->n + f[1];
-    b.max_depth = f[2];
-    if (f[0] & 2u) {
-        b.built = false;
-        return nb_fail(ctx, NB_ERR_NODE_POOL, "octree needs %llu internal nodes, pool holds %llu (storage_size_param=%d)",
-                       (unsigned long long) f[1], (unsigned long long) (b.cap_nodes - ctx->n), ctx->cfg.storage_size_param);
+    if (b.built) {
+        b.num_internal = f[1];
+        b.num_nodes = ctx->n + f[1];
+        b.max_depth = f[2];
     }
-    if (f[0] & 1u) {
-        b.built = false;
-        return nb_fail(ctx, NB_ERR_TREE_DEPTH, "octree deeper than %d levels: coincident bodies are not supported (reference: unbounded splitting)",
-                       NB_MAX_TREE_DEPTH);
-    }
-    return NB_OK;
+    // f[0]: the latest build; f[4]: every build since the last report (a build that failed in the middle of a batch of
+    // steps left zero accelerations for that step, and the builds after it cleared f[0])
+    const uint32_t bits = f[0] | f[4];
+    if (!bits) return NB_OK;
+    if (f[4]) NB_CUDA(ctx, cudaMemset(b.dev_flags + 4, 0, sizeof(uint32_t)));   // reported once
+    if (f[0]) b.built = false;
+    const char *when = f[0] ? "" : " (in an earlier step of this batch; that step used zero accelerations)";
+    if (bits & 2u)
+        return nb_fail(ctx, NB_ERR_NODE_POOL, "octree needs %llu internal nodes, pool holds %llu (storage_size_param=%d)%s",
+                       (unsigned long long) f[1], (unsigned long long) (b.cap_nodes - ctx->n), ctx->cfg.storage_size_param, when);
+    return nb_fail(ctx, NB_ERR_TREE_DEPTH, "octree deeper than %d levels: coincident bodies are not supported (reference: unbounded splitting)%s",
+                   NB_MAX_TREE_DEPTH, when);
 }
 
 int nb_bh_aabb(nb_ctx *ctx, double out[7]) {
@@ -698,7 +812,7 @@ bool canon_rec(const HostTree &t, uint32_t node, int depth, uint64_t phi, uint64
     for (uint32_t c = node + 1; c < m.x;) {
         const uint2 mc = t.meta[c];
         if (mc.x <= c || mc.x > m.x) return false;
-        child_of_octant[rank_to_octant((mc.y >> NB_DIGIT_SHIFT) & 7u)] = c;
+        child_of_octant[rank_to_octant(nb_meta_rank(mc.y))] = c;
         c = mc.x;
     }
     const double h = edge / 2;  // ParallelOctreeTopDownSubtrees.cpp:256

@@ -154,31 +154,69 @@ __device__ __forceinline__ uint64_t key_lo_of(double px, double py, double pz, c
     return descend21(px, py, pz, mnx, mny, mnz, edge);
 }
 
-// ---- 2b. order equal-key_hi runs by the lower key word ---------------------------------------------------------------------
+// ---- 2b. after the sort: slots and full keys of the packed words; order runs the sort left undecided ----------------------
+// packed words (scan_sort.cuh os_pack) in sorted order -> perm (storage slot of sorted body i) and the body's full key
 __global__ void __launch_bounds__(256)
-fix_ties_kernel(const uint64_t *__restrict__ hi_sorted, const double *__restrict__ x, const double *__restrict__ y,
-                const double *__restrict__ z, const double *__restrict__ aabb, uint32_t *__restrict__ perm, uint64_t n,
-                uint32_t *__restrict__ flags) {
+unpack_kernel(const uint64_t *__restrict__ words, const uint64_t *__restrict__ key_by_slot, uint64_t n, int idx_bits,
+              uint32_t *__restrict__ perm, uint64_t *__restrict__ hi_sorted) {
+    const uint64_t i = (uint64_t) blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const uint32_t p = (uint32_t) (words[i] & ((1ull << idx_bits) - 1ull));
+    perm[i] = p;
+    hi_sorted[i] = key_by_slot[p];
+}
+
+#define NB_PACKED_KEY_SHIFT 23   /* a 5-pass packed sort orders the upper 40 of the 63 key bits: bits 23..62 */
+#define NB_PACKED_RUN_LIMIT 64   /* longer undecided runs make the host switch to the full 8-pass sort */
+
+// Bodies whose keys agree above `run_shift` form a run the sort left in slot order (run_shift = 23 after the packed
+// sort, 0 after the full sort: only bodies closer than edge * 2^-21 remain).  The head of each run orders it by the
+// full (key_hi, key_lo) with an insertion sort -- runs are rare and short (two or three bodies) unless thousands of
+// bodies share a 13-level cell, which flags[3] reports so that the host uses the full sort from the next build on.
+// key_lo (levels 21..41) is computed on demand, only for bodies that agree on all of key_hi.
+__global__ void __launch_bounds__(256)
+tie_fix_kernel(uint64_t *__restrict__ hi_sorted, const double *__restrict__ x, const double *__restrict__ y,
+               const double *__restrict__ z, const double *__restrict__ aabb, uint32_t *__restrict__ perm, uint64_t n,
+               int run_shift, uint32_t *__restrict__ flags) {
     const uint64_t i = (uint64_t) blockIdx.x * blockDim.x + threadIdx.x;
     if (i + 1 >= n) return;
-    const uint64_t k = hi_sorted[i];
-    if (hi_sorted[i + 1] != k) return;
-    if (i > 0 && hi_sorted[i - 1] == k) return;
+    const uint64_t hi_i = hi_sorted[i];
+    // statistic for the host's choice of sort: longest run of equal upper-40-bit prefixes, counted up to the limit + 1
+    {
+        const uint64_t k40 = hi_i >> NB_PACKED_KEY_SHIFT;
+        if ((hi_sorted[i + 1] >> NB_PACKED_KEY_SHIFT) == k40 && (i == 0 || (hi_sorted[i - 1] >> NB_PACKED_KEY_SHIFT) != k40)) {
+            uint32_t len = 2;
+            while (len <= NB_PACKED_RUN_LIMIT && i + len < n && (hi_sorted[i + len] >> NB_PACKED_KEY_SHIFT) == k40) ++len;
+            if (len > *(volatile uint32_t *) &flags[3]) atomicMax(&flags[3], len);
+        }
+    }
+    const uint64_t k = hi_i >> run_shift;
+    if ((hi_sorted[i + 1] >> run_shift) != k) return;
+    if (i > 0 && (hi_sorted[i - 1] >> run_shift) == k) return;
     uint64_t e = i + 1;
-    while (e + 1 < n && hi_sorted[e + 1] == k) ++e;
-    for (uint64_t a = i + 1; a <= e; ++a) {  // insertion sort of the run by the lower key word
+    while (e + 1 < n && (hi_sorted[e + 1] >> run_shift) == k) ++e;
+    for (uint64_t a = i + 1; a <= e; ++a) {  // insertion sort of the run by (key_hi, key_lo)
         const uint32_t pa = perm[a];
-        const uint64_t la = key_lo_of(x[pa], y[pa], z[pa], aabb);
+        const uint64_t ha = hi_sorted[a];
+        uint64_t la = 0;
+        bool have_la = false;
         uint64_t b = a;
         while (b > i) {
+            const uint64_t hb = hi_sorted[b - 1];
+            if (hb < ha) break;
             const uint32_t pb = perm[b - 1];
-            const uint64_t lb = key_lo_of(x[pb], y[pb], z[pb], aabb);
-            if (lb == la) atomicOr(&flags[0], NB_FLAG_DEPTH);  // identical 42-level paths: coincident bodies
-            if (lb <= la) break;
+            if (hb == ha) {
+                if (!have_la) { la = key_lo_of(x[pa], y[pa], z[pa], aabb); have_la = true; }
+                const uint64_t lb = key_lo_of(x[pb], y[pb], z[pb], aabb);
+                if (lb == la) atomicOr(&flags[0], NB_FLAG_DEPTH);  // identical 42-level paths: coincident bodies
+                if (lb <= la) break;
+            }
             perm[b] = pb;
+            hi_sorted[b] = hb;
             --b;
         }
         perm[b] = pa;
+        hi_sorted[b] = ha;
     }
 }
 
@@ -199,13 +237,14 @@ struct reorder_args {
     double *dst[10];
 };
 __global__ void __launch_bounds__(256)
-reorder_kernel(const uint32_t *__restrict__ perm, uint64_t n, reorder_args a, const uint32_t *__restrict__ id_in,
+reorder_kernel(const uint32_t *__restrict__ perm, uint64_t n, int count, reorder_args a, const uint32_t *__restrict__ id_in,
                uint32_t *__restrict__ id_out, int identity) {
     const uint64_t i = (uint64_t) blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     const uint32_t p = perm[i];
 #pragma unroll
-    for (int k = 0; k < 10; ++k) a.dst[k][i] = a.src[k][p];
+    for (int k = 0; k < 10; ++k)
+        if (k < count) a.dst[k][i] = a.src[k][p];
     id_out[i] = identity ? p : id_in[p];
 }
 
@@ -304,7 +343,7 @@ emit_kernel(const uint64_t *__restrict__ hi, const uint64_t *__restrict__ lo, co
         const uint64_t node = head + k;
         const uint64_t skip = r + 1 < n ? (r + 1) + base[r + 1] : M;
         const uint32_t dig = d > 0 ? digit_at(hi_i, lo_i, d - 1) : 0u;  // visit rank of this cell inside its parent
-        meta[node] = make_uint2((uint32_t) skip, (dig << NB_DIGIT_SHIFT) | (uint32_t) d);
+        meta[node] = make_uint2((uint32_t) skip, ((uint32_t) d << NB_DEPTH_SHIFT) | dig);
         body_count[node] = (uint32_t) (r - i + 1);
     }
     const int leaf_parent_depth = d_cur > d_prev ? d_cur : d_prev;  // -1 only when N == 1
@@ -391,10 +430,13 @@ __device__ __forceinline__ void store_node(double *com, double *msum4, uint32_t 
 }
 
 __global__ void __launch_bounds__(256)
-com_leaf_kernel(uint64_t n, const uint32_t *__restrict__ flags_in, const double *__restrict__ px,
+com_leaf_kernel(uint64_t n, uint32_t *flags_in, const double *__restrict__ px,
                 const double *__restrict__ py, const double *__restrict__ pz, const double *__restrict__ pm,
                 const uint32_t *__restrict__ leaf_node, double *__restrict__ com, double *__restrict__ msum4) {
     const uint64_t i = (uint64_t) blockIdx.x * blockDim.x + threadIdx.x;
+    // every kernel that can raise an error bit of this build has run: keep the bits in the sticky word, which the next
+    // build does not clear (a failed build inside a batch of steps must still be reported at the end of the batch)
+    if (i == 0 && flags_in[0]) atomicOr(&flags_in[4], flags_in[0]);
     if (i >= n || (flags_in[0] & NB_FLAG_POOL)) return;
     const double m = pm[i];
     store_node(com, msum4, leaf_node[i], __dmul_rn(px[i], m), __dmul_rn(py[i], m), __dmul_rn(pz[i], m), m);
@@ -405,7 +447,7 @@ com_leaf_kernel(uint64_t n, const uint32_t *__restrict__ flags_in, const double 
 template <bool COHERENT>
 __device__ __forceinline__ void com_level(int depth, const uint32_t *__restrict__ level, const uint32_t *__restrict__ list,
                                           const uint2 *__restrict__ meta, double *com, double *msum4,
-                                          uint32_t *__restrict__ ctab, uint32_t tid, uint32_t nthreads) {
+                                          uint32_t tid, uint32_t nthreads) {
     const uint32_t count = level[depth];
     const uint32_t *nodes = list + level[NB_LEVELS + depth];
     for (uint32_t k = tid; k < count; k += nthreads) {
@@ -418,7 +460,7 @@ __device__ __forceinline__ void com_level(int depth, const uint32_t *__restrict_
         uint32_t ch = p + 1;
         while (ch < end) {
             const uint2 mc = meta[ch];
-            const uint32_t rank = (mc.y >> NB_DIGIT_SHIFT) & 7u;
+            const uint32_t rank = nb_meta_rank(mc.y);
 #pragma unroll
             for (int r = 0; r < 8; ++r)
                 if (rank == (uint32_t) r) child[r] = ch;
@@ -441,22 +483,16 @@ __device__ __forceinline__ void com_level(int depth, const uint32_t *__restrict_
             }
         }
         store_node(com, msum4, p, cx, cy, cz, sumMasses);
-        if (ctab) {  // child table by visit rank
-            uint4 *ct = reinterpret_cast<uint4 *>(ctab) + 2 * (size_t) p;
-            ct[0] = make_uint4(child[0], child[1], child[2], child[3]);
-            ct[1] = make_uint4(child[4], child[5], child[6], child[7]);
-        }
     }
 }
 
 // one launch per level (fallback when a cooperative launch is not possible)
 __global__ void __launch_bounds__(256)
 com_level_kernel(int depth, const uint32_t *__restrict__ flags_in, const uint32_t *__restrict__ level,
-                 const uint32_t *__restrict__ list, const uint2 *__restrict__ meta, double *com, double *msum4,
-                 uint32_t *__restrict__ ctab /* optional child table for the group traversal */) {
+                 const uint32_t *__restrict__ list, const uint2 *__restrict__ meta, double *com, double *msum4) {
     // flags[2] = deepest leaf = 1 + deepest internal node: nothing to do for the levels below the tree
     if ((uint32_t) depth >= flags_in[2] || (flags_in[0] & NB_FLAG_POOL)) return;
-    com_level<false>(depth, level, list, meta, com, msum4, ctab, blockIdx.x * blockDim.x + threadIdx.x, gridDim.x * blockDim.x);
+    com_level<false>(depth, level, list, meta, com, msum4, blockIdx.x * blockDim.x + threadIdx.x, gridDim.x * blockDim.x);
 }
 
 // All levels in ONE cooperative launch: the grid is resident as a whole and walks the levels from the deepest internal
@@ -464,14 +500,14 @@ com_level_kernel(int depth, const uint32_t *__restrict__ flags_in, const uint32_
 // work-group, BarnesHutOctree.cpp:327-383).  Replaces 42 dependent launches, most of them for levels below the tree.
 __global__ void __launch_bounds__(256)
 com_levels_kernel(const uint32_t *__restrict__ flags_in, const uint32_t *__restrict__ level, const uint32_t *__restrict__ list,
-                  const uint2 *__restrict__ meta, double *com, double *msum4, uint32_t *__restrict__ ctab) {
+                  const uint2 *__restrict__ meta, double *com, double *msum4) {
     if (flags_in[0] & NB_FLAG_POOL) return;   // the same decision in every CTA
     cooperative_groups::grid_group grid = cooperative_groups::this_grid();
     int depth = (int) flags_in[2] - 1;
     if (depth > NB_MAX_TREE_DEPTH - 1) depth = NB_MAX_TREE_DEPTH - 1;
     const uint32_t tid = blockIdx.x * blockDim.x + threadIdx.x, nthreads = gridDim.x * blockDim.x;
     for (; depth >= 0; --depth) {
-        com_level<true>(depth, level, list, meta, com, msum4, ctab, tid, nthreads);
+        com_level<true>(depth, level, list, meta, com, msum4, tid, nthreads);
         if (depth > 0) grid.sync();
     }
 }
@@ -491,6 +527,8 @@ int nbk_bh_reserve(nb_ctx *ctx) {
     const uint64_t nb = n + 32;
     NB_CHECK(nb_alloc(ctx, &b.key_hi, nb));
     NB_CHECK(nb_alloc(ctx, &b.key_hi_alt, nb));
+    NB_CHECK(nb_alloc(ctx, &b.word_a, nb));
+    NB_CHECK(nb_alloc(ctx, &b.word_b, nb));
     NB_CHECK(nb_alloc(ctx, &b.perm, nb));
     NB_CHECK(nb_alloc(ctx, &b.perm_alt, nb));
     NB_CHECK(nb_alloc(ctx, &b.delta, nb));
@@ -504,12 +542,17 @@ int nbk_bh_reserve(nb_ctx *ctx) {
     NB_CHECK(nb_alloc(ctx, &b.level, 3 * NB_LEVELS));
     NB_CHECK(nb_alloc(ctx, &b.level_list, cap_nodes - n + 8));
     NB_CHECK(nb_alloc(ctx, &b.body_count, cap_nodes));
-    const size_t scratch = std::max(nbprim::rs_scratch_elems(nb), nbprim::os_scratch_elems(nb)) + nbprim::scan_tiles_for(nb) + 64;
+    const size_t scratch = nbprim::os_scratch_elems(nb) + nbprim::scan_tiles_for(nb) + 64;
     NB_CHECK(nb_alloc(ctx, &b.hist, scratch));
     NB_CHECK(nb_alloc(ctx, &b.aabb_dev, 8));
     NB_CHECK(nb_alloc(ctx, &b.aabb_partial, 6 * 1024));
     NB_CHECK(nb_alloc(ctx, &b.dev_flags, 8 + 1024));   // 8 flag words + per-SM tile counters of the traversal
     NB_CHECK(nb_alloc(ctx, &b.stat_totals, 8));
+    if (!b.stat_host) {
+        NB_CUDA(ctx, cudaMallocHost((void **) &b.stat_host, 4 * sizeof(uint32_t)));
+        NB_CUDA(ctx, cudaEventCreateWithFlags(&b.stat_event, cudaEventDisableTiming));
+    }
+    b.stat_pending = b.stat_known = b.long_runs = false;   // a new problem size: nothing is known about its distribution
     NB_CUDA(ctx, cudaMemsetAsync(b.dev_flags, 0, 8 * sizeof(uint32_t), ctx->stream));
     b.cap_bodies = n;
     b.cap_nodes = cap_nodes;
@@ -519,12 +562,18 @@ int nbk_bh_reserve(nb_ctx *ctx) {
 
 void nbk_bh_release(nb_ctx *ctx) {
     nb_bh_state &b = ctx->bh;
-    nb_free(&b.key_hi); nb_free(&b.key_hi_alt); nb_free(&b.perm); nb_free(&b.perm_alt);
+    nb_free(&b.key_hi); nb_free(&b.key_hi_alt); nb_free(&b.word_a); nb_free(&b.word_b); nb_free(&b.perm); nb_free(&b.perm_alt);
     nb_free(&b.delta); nb_free(&b.chain_cnt);
     nb_free(&b.chain_base); nb_free(&b.leaf_node); 
-    nb_free(&b.visits); nb_free(&b.com); nb_free(&b.msum); nb_free(&b.meta); nb_free(&b.level); nb_free(&b.level_list); nb_free(&b.ctab); 
+    nb_free(&b.visits); nb_free(&b.com); nb_free(&b.msum); nb_free(&b.meta); nb_free(&b.level); nb_free(&b.level_list);
     nb_free(&b.body_count); nb_free(&b.hist); nb_free(&b.aabb_dev);
     nb_free(&b.aabb_partial); nb_free(&b.dev_flags); nb_free(&b.stat_totals);
+    if (b.stat_host) {
+        cudaStreamSynchronize(ctx->stream);   // a pending read-back of the statistic targets stat_host
+        cudaFreeHost(b.stat_host); b.stat_host = nullptr;
+        cudaEventDestroy(b.stat_event); b.stat_event = nullptr;
+    }
+    b.stat_pending = b.stat_known = b.long_runs = false;
     b.cap_bodies = b.cap_nodes = 0;
     b.built = false;
 }
@@ -540,6 +589,21 @@ int nbk_bh_aabb(nb_ctx *ctx) {
     aabb_final_kernel<<<1, 256, 0, ctx->stream>>>(b.aabb_partial, blocks, b.aabb_dev);
     NB_LAUNCH_CHECK(ctx);
     return NB_OK;
+}
+
+// Packed or full sort for this build (see nbk_bh_build).  The statistic of the latest finished build arrives through a
+// pinned word and an event; nothing here waits for the device.
+static bool bh_choose_packed_sort(nb_ctx *ctx) {
+    nb_bh_state &b = ctx->bh;
+    const int forced = ctx->cfg.reserved[6];
+    if (forced == 1) return false;
+    if (forced == 2) return true;
+    if (b.stat_pending && !ctx->capturing && cudaEventQuery(b.stat_event) == cudaSuccess) {
+        b.stat_pending = false;
+        b.stat_known = true;
+        b.long_runs = b.stat_host[0] > NB_PACKED_RUN_LIMIT;
+    }
+    return b.stat_known && !b.long_runs;
 }
 
 int nbk_bh_build(nb_ctx *ctx) {
@@ -562,30 +626,46 @@ int nbk_bh_build(nb_ctx *ctx) {
         nb_timer_scope t(ctx, NB_T_KEYS_SORT);
         keys_kernel<<<g256, 256, 0, ctx->stream>>>(ctx->x, ctx->y, ctx->z, n, b.aabb_dev, b.key_hi);
         NB_LAUNCH_CHECK(ctx);
-        // cfg.reserved[6] (sort_variant): 0 = one-sweep sort (all-pass histogram + decoupled look-back, one kernel per
-        // pass), 1 = the earlier three-kernels-per-pass form (A/B); both are the same stable sort
-        if (ctx->cfg.reserved[6] == 1)
-            NB_CHECK(nbprim::radix_sort_pairs(ctx, b.key_hi, b.perm, b.key_hi_alt, b.perm_alt, n, 63, b.hist, &hi_sorted,
-                                              &perm_sorted, true));
-        else
+        // Two forms of the same sort (cfg.reserved[6], sort_variant: 0 = chosen per build, 1 = full, 2 = packed):
+        //   packed: one 64-bit word {upper key bits | storage slot} per body, 5 one-sweep passes over its upper 40 bits
+        //           (13 octree levels), 16 B per body and pass; the few bodies that share a 13-level cell are then
+        //           ordered from their full keys by tie_fix_kernel;
+        //   full:   (key, slot) pairs, 8 passes over all 63 key bits, 24 B per body and pass.
+        // Both end in the same order.  The packed form is what a step uses; the full form takes over when the previous
+        // build reported a long undecided run (a cluster far denser than the box: flags[3], read back asynchronously),
+        // and for the first build of a context, whose distribution nobody has seen yet.
+        const bool packed = bh_choose_packed_sort(ctx);
+        if (packed) {
+            int idx_bits = 1;
+            while ((1ull << idx_bits) < n) ++idx_bits;
+            uint64_t *ws = nullptr;
+            NB_CHECK(nbprim::onesweep_sort_packed(ctx, b.key_hi, b.word_a, b.word_b, n, idx_bits, 5, b.hist, &ws));
+            unpack_kernel<<<g256, 256, 0, ctx->stream>>>(ws, b.key_hi, n, idx_bits, b.perm, b.key_hi_alt);
+            NB_LAUNCH_CHECK(ctx);
+            hi_sorted = b.key_hi_alt;
+            perm_sorted = b.perm;
+        } else {
             NB_CHECK(nbprim::onesweep_sort_pairs(ctx, b.key_hi, b.perm, b.key_hi_alt, b.perm_alt, n, 63, b.hist, &hi_sorted,
                                                  &perm_sorted, true));
-        fix_ties_kernel<<<g256, 256, 0, ctx->stream>>>(hi_sorted, ctx->x, ctx->y, ctx->z, b.aabb_dev, perm_sorted, n,
-                                                       b.dev_flags);
+        }
+        tie_fix_kernel<<<g256, 256, 0, ctx->stream>>>(hi_sorted, ctx->x, ctx->y, ctx->z, b.aabb_dev, perm_sorted, n,
+                                                      packed ? NB_PACKED_KEY_SHIFT : 0, b.dev_flags);
         NB_LAUNCH_CHECK(ctx);
         // key_hi_alt / perm_alt are reused below: make the sorted data live in (key_hi, perm)
-        if (hi_sorted != b.key_hi) {
-            uint64_t *tk = b.key_hi; b.key_hi = b.key_hi_alt; b.key_hi_alt = tk;
-            uint32_t *tp = b.perm; b.perm = b.perm_alt; b.perm_alt = tp;
-        }
-        // move the whole state into sorted order; the arrays swap roles with their partners
+        if (hi_sorted != b.key_hi) { uint64_t *tk = b.key_hi; b.key_hi = b.key_hi_alt; b.key_hi_alt = tk; }
+        if (perm_sorted != b.perm) { uint32_t *tp = b.perm; b.perm = b.perm_alt; b.perm_alt = tp; }
+        // move the whole state into sorted order; the arrays swap roles with their partners.  Accelerations that belong
+        // to earlier positions (the integrator has consumed them; the walk that follows overwrites them) stay behind:
+        // 7 arrays instead of 10
         {
             double **cur[10] = {&ctx->m, &ctx->x, &ctx->y, &ctx->z, &ctx->vx, &ctx->vy, &ctx->vz, &ctx->ax, &ctx->ay, &ctx->az};
+            const int count = ctx->a_fresh ? 10 : 7;
+            if (!ctx->a_fresh) ctx->a_order_ok = false;
             reorder_args ra;
             for (int k = 0; k < 10; ++k) { ra.src[k] = *cur[k]; ra.dst[k] = ctx->alt[k]; }
-            reorder_kernel<<<g256, 256, 0, ctx->stream>>>(b.perm, n, ra, ctx->id, ctx->id_alt, ctx->identity_order ? 1 : 0);
+            reorder_kernel<<<g256, 256, 0, ctx->stream>>>(b.perm, n, count, ra, ctx->id, ctx->id_alt, ctx->identity_order ? 1 : 0);
             NB_LAUNCH_CHECK(ctx);
-            for (int k = 0; k < 10; ++k) { double *t = *cur[k]; *cur[k] = ctx->alt[k]; ctx->alt[k] = t; }
+            for (int k = 0; k < count; ++k) { double *t = *cur[k]; *cur[k] = ctx->alt[k]; ctx->alt[k] = t; }
             uint32_t *ti = ctx->id; ctx->id = ctx->id_alt; ctx->id_alt = ti;
             ctx->identity_order = false;
         }
@@ -617,9 +697,6 @@ int nbk_bh_build(nb_ctx *ctx) {
         com_leaf_kernel<<<g256, 256, 0, ctx->stream>>>(n, b.dev_flags, ctx->x, ctx->y, ctx->z, ctx->m, b.leaf_node, b.com, b.msum);
         NB_LAUNCH_CHECK(ctx);
         const unsigned level_grid = (unsigned) std::min<uint64_t>(g256, (uint64_t) ctx->sm_count * 32);
-        const bool want_ctab = ctx->cfg.reserved[1] == 3;
-        if (want_ctab && !b.ctab) NB_CHECK(nb_alloc(ctx, &b.ctab, 8 * b.cap_nodes));
-        b.ctab_valid = want_ctab;
         // cfg.reserved[7] (com_variant): 0 = all levels in one cooperative launch, 1 = one launch per level (A/B, and the
         // fallback when the device or the driver refuses the cooperative launch)
         bool done = false;
@@ -634,8 +711,7 @@ int nbk_bh_build(nb_ctx *ctx) {
             const uint32_t *a_flags = b.dev_flags, *a_level = b.level, *a_list = b.level_list;
             const uint2 *a_meta = b.meta;
             double *a_com = b.com, *a_msum = b.msum;
-            uint32_t *a_ctab = want_ctab ? b.ctab : nullptr;
-            void *args[] = {&a_flags, &a_level, &a_list, &a_meta, &a_com, &a_msum, &a_ctab};
+            void *args[] = {&a_flags, &a_level, &a_list, &a_meta, &a_com, &a_msum};
             const cudaError_t e = cudaLaunchCooperativeKernel((const void *) com_levels_kernel, dim3(cgrid), dim3(256), args, 0, ctx->stream);
             if (e == cudaSuccess) {
                 ctx->launches++;
@@ -648,10 +724,15 @@ int nbk_bh_build(nb_ctx *ctx) {
         if (!done) {
             for (int depth = NB_MAX_TREE_DEPTH - 1; depth >= 0; --depth) {
                 com_level_kernel<<<level_grid, 256, 0, ctx->stream>>>(depth, b.dev_flags, b.level, b.level_list, b.meta, b.com,
-                                                                      b.msum, want_ctab ? b.ctab : nullptr);
+                                                                      b.msum);
                 NB_LAUNCH_CHECK(ctx);
             }
         }
+    }
+    if (!ctx->capturing && !b.stat_pending) {   // longest undecided run of this build -> the next builds' choice of sort
+        NB_CUDA(ctx, cudaMemcpyAsync(b.stat_host, b.dev_flags + 3, sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
+        NB_CUDA(ctx, cudaEventRecord(b.stat_event, ctx->stream));
+        b.stat_pending = true;
     }
     b.built = true;
     return NB_OK;

@@ -9,6 +9,7 @@
 #include "../../include/nbody_b200.h"
 
 #define NB_SM_COUNT_FALLBACK 148
+#define NB_MAX_PEERS 8
 
 // Packed source record of the all-pairs kernel: one 48-byte AoS entry per source body so a whole tile is a
 // single contiguous TMA bulk copy.  c1 = 1.5*m and c2 = 1.875*m are the Taylor coefficients of
@@ -22,16 +23,24 @@ struct __align__(16) nb_src_rec {
 // [2,0,3,1,6,4,7,5], BarnesHutAlgorithm.cpp:370-385).  40 bytes of traversal payload per node:
 //   com[4*n+0..2] = centre of mass (already divided by the mass), com[4*n+3] = mass     (32 B)
 //   meta[n].x     = index of the first node AFTER this node's subtree ("skip link")
-//   meta[n].y     = bit 31: body leaf; bits 28-30: visit rank of the node inside its parent;
-//                   bits 0-27: sorted index of the body (leaf) or depth (internal node)              ( 8 B)
+//   meta[n].y     = body leaf:     bit 31 | visit rank of the node inside its parent << 28 | sorted index of the body
+//                   internal node: depth << 21 | visit rank (bits 0-2).  The walk adds this word to the high word of
+//                   a squared distance: depth << 21 is the exponent shift of 4^depth, the rank only widens the
+//                   undecided band of the acceptance test (bh_traverse.cu)                             ( 8 B)
 #define NB_LEAF_FLAG 0x80000000u
 #define NB_DIGIT_SHIFT 28
 #define NB_PAYLOAD_MASK 0x0fffffffu
+#define NB_DEPTH_SHIFT 21
+static __host__ __device__ __forceinline__ uint32_t nb_meta_rank(uint32_t y) {
+    return (y & NB_LEAF_FLAG) ? (y >> NB_DIGIT_SHIFT) & 7u : y & 7u;
+}
+static __host__ __device__ __forceinline__ uint32_t nb_meta_depth(uint32_t y) { return y >> NB_DEPTH_SHIFT; }  // internal nodes
 
 struct nb_bh_state {
     // per-body, sorted order
     uint64_t *key_hi = nullptr;                              // octant-path key, levels 0..20 (visit-rank digits)
     uint64_t *key_hi_alt = nullptr;                          // radix sort ping-pong; after the sort: key word of levels 21..41 (where needed)
+    uint64_t *word_a = nullptr, *word_b = nullptr;           // packed sort words {upper key bits | storage slot}, ping-pong
     uint32_t *perm = nullptr, *perm_alt = nullptr;           // sorted index -> storage slot before this build's reorder
     int32_t *delta = nullptr;                                // common-prefix digits of sorted neighbours (i, i+1)
     uint32_t *chain_cnt = nullptr, *chain_base = nullptr;    // internal nodes starting at body i, and their scan
@@ -41,7 +50,6 @@ struct nb_bh_state {
     double *msum = nullptr;                                  // 4 doubles per node: {sum m*x, sum m*y, sum m*z, sum m} (reference's massCenters_* / sumOfMasses)
     uint2 *meta = nullptr;
     uint32_t *level = nullptr, *level_list = nullptr;        // per-depth internal-node lists (count / start / cursor, nodes)
-    uint32_t *ctab = nullptr;                                // 8 child node indices per node, by visit rank (NB_NONE = empty octant)
     uint32_t *body_count = nullptr;
     // sort scratch
     uint32_t *hist = nullptr;
@@ -53,13 +61,17 @@ struct nb_bh_state {
     // device scalars
     double *aabb_dev = nullptr;                              // 7 doubles: min xyz, max xyz, edge
     double *aabb_partial = nullptr;
-    uint32_t *dev_flags = nullptr;                           // [0] error bits (1 depth, 2 pool), [1] internal node count, [2] max depth
+    uint32_t *dev_flags = nullptr;                           // [0] error bits of the latest build (1 depth, 2 pool), [1] internal node count,
+                                                             // [2] max depth, [3] longest run the packed sort leaves undecided (capped),
+                                                             // [4] error bits of all builds since they were last reported (sticky)
+    uint32_t *stat_host = nullptr;                           // pinned copy of dev_flags[3] of the latest finished build
+    cudaEvent_t stat_event = nullptr;
+    bool stat_pending = false, stat_known = false, long_runs = false;
     uint64_t cap_bodies = 0, cap_nodes = 0;
     uint64_t num_nodes = 0, num_internal = 0;
     uint32_t max_depth = 0;
     double aabb[7] = {0, 0, 0, 0, 0, 0, 0};
     bool built = false;
-    bool ctab_valid = false;
     bool stats_enabled = false;
 };
 
@@ -79,6 +91,14 @@ struct nb_ctx {
     double *vx = nullptr, *vy = nullptr, *vz = nullptr;
     double *ax = nullptr, *ay = nullptr, *az = nullptr;
     double *alt[10] = {};            // ping-pong partners of m,x,y,z,vx,vy,vz,ax,ay,az (also scratch for read-back)
+    // All 21 arrays above (10 + 10 partners + anorm) are carved out of ONE allocation, so that a peer GPU's copy of any of
+    // them is "peer slab base + the same byte offset" (multi-GPU: the walk stores its results straight into every
+    // rank's arrays over NVLink, bh_traverse.cu).
+    unsigned char *slab = nullptr;
+    size_t slab_bytes = 0;
+    // accelerations: computed for the current positions and stored in the current storage order?  Both turn false when
+    // the positions advance / a build leaves them behind (the permutation skips arrays nobody will read).
+    bool a_fresh = false, a_order_ok = true;
     uint32_t *id = nullptr, *id_alt = nullptr;
     bool identity_order = true;
     double *anorm = nullptr;
@@ -106,9 +126,21 @@ struct nb_ctx {
     const void *graph_ptrs[8] = {};
     uint64_t graph_launches = 0;      // kernel launches one replay stands for
     bool graph_unusable = false;      // the period-two assumption did not hold: stay on the eager path
+    bool capturing = false;           // inside the stream capture of nb_advance: no host-visible side effects
     // comm
     void *nccl_comm = nullptr;
     int world = 1, rank = 0;
+    // peer slabs mapped with CUDA IPC (index = rank; own entry = slab); p2p_ok: every rank mapped every peer
+    unsigned char *peer_slab[NB_MAX_PEERS] = {};
+    bool p2p_ok = false;
+    double *barrier_word = nullptr;   // one device double for the NCCL barrier (all-reduce of nothing)
+};
+
+// what a kernel needs to store into every rank's copy of an array: p-th copy of local pointer q is
+// base[p] + ((unsigned char *) q - base[rank])
+struct nb_peer_table {
+    int world, rank;
+    unsigned char *base[NB_MAX_PEERS];
 };
 
 int nb_fail(nb_ctx *ctx, int status, const char *fmt, ...);
@@ -175,6 +207,11 @@ int nbk_unpermute(nb_ctx *ctx, int count, const double *const *src, double *cons
 int nbk_permute_in(nb_ctx *ctx, int count, const double *const *src, double *const *dst);
 int nbk_comm_allgather_accel(nb_ctx *ctx, double *ax, double *ay, double *az, uint64_t n);
 void nbk_comm_destroy(nb_ctx *ctx);
+int nbk_comm_barrier(nb_ctx *ctx);              // stream-ordered barrier over all ranks (no-op on one rank)
+int nbk_comm_map_peers(nb_ctx *ctx);            // collective: exchange the slab handles, map the peers' slabs
+void nbk_comm_unmap_peers(nb_ctx *ctx);         // collective when peers were mapped (ends with a barrier)
+nb_peer_table nbk_peer_table(const nb_ctx *ctx);
+int nbk_bh_accel_fused(nb_ctx *ctx, uint64_t s_begin, uint64_t s_end, int epilogue, double dt, bool to_peers);
 int nbk_comm_allreduce_sum(nb_ctx *ctx, double *buf, size_t count);
 
 // ---- device helpers ------------------------------------------------------------------------------------------

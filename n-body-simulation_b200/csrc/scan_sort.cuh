@@ -1,6 +1,5 @@
 // Hand-written device primitives used by the Barnes-Hut build: exclusive prefix sum over uint32 and a stable
-// LSD radix sort of (uint64 key, uint32 value) pairs (one-sweep form with decoupled look-back, plus the earlier
-// histogram / scan / scatter form kept for A/B runs).  Replaces the reference's serial single_task scan
+// LSD radix sort of (uint64 key, uint32 value) pairs or of packed 64-bit words (one-sweep form, decoupled look-back).  Replaces the reference's serial single_task scan
 // (ParallelOctreeTopDownSubtrees.cpp:461-474), its O(S^2) prefix (:491-500) and the linear-search scatter (:512-532).
 #pragma once
 #include "common.cuh"
@@ -115,166 +114,35 @@ inline int exclusive_scan_u32(nb_ctx *ctx, const uint32_t *in, uint32_t *out, ui
     return NB_OK;
 }
 
-// ---------------------------------------------------------------------------------------------------------------
-// Stable LSD radix sort, 8-bit digits.  Per pass: (1) per-tile digit histogram, (2) exclusive scan of the
-// digit-major histogram table, (3) stable scatter (warp-level MATCH.ANY ranking, warp-private counters).
-// ---------------------------------------------------------------------------------------------------------------
-constexpr int RS_THREADS = 256;
-constexpr int RS_WARPS = RS_THREADS / 32;
-constexpr int RS_ITEMS = 8;                       // keys per thread
-constexpr int RS_TILE = RS_THREADS * RS_ITEMS;    // 2048 keys per block
-constexpr int RS_BINS = 256;
-
-__global__ void __launch_bounds__(RS_THREADS)
-rs_hist_kernel(const uint64_t *__restrict__ keys, uint64_t n, int shift, uint32_t n_tiles,
-               uint32_t *__restrict__ hist /* [RS_BINS][n_tiles] */) {
-    __shared__ uint32_t h[RS_BINS];
-    h[threadIdx.x] = 0;
-    __syncthreads();
-    const uint64_t base = (uint64_t) blockIdx.x * RS_TILE;
-#pragma unroll 4
-    for (int k = 0; k < RS_ITEMS; ++k) {
-        const uint64_t i = base + (uint64_t) k * RS_THREADS + threadIdx.x;
-        if (i < n) atomicAdd(&h[(keys[i] >> shift) & 0xff], 1u);
-    }
-    __syncthreads();
-    hist[(size_t) threadIdx.x * n_tiles + blockIdx.x] = h[threadIdx.x];
-}
-
-template <bool IOTA_VALS>
-__global__ void __launch_bounds__(RS_THREADS)
-rs_scatter_kernel(const uint64_t *__restrict__ keys_in, const uint32_t *__restrict__ vals_in, uint64_t n, int shift,
-                  uint32_t n_tiles, const uint32_t *__restrict__ hist_scanned, uint64_t *__restrict__ keys_out,
-                  uint32_t *__restrict__ vals_out) {
-    __shared__ uint32_t cnt[RS_WARPS][RS_BINS];   // per-warp digit counts, then per-warp exclusive bases inside the tile
-    __shared__ uint32_t gbase[RS_BINS];           // global start of (digit, this tile) minus the digit's start in the tile
-    __shared__ uint64_t skey[RS_TILE];            // tile staged in digit order so the global writes are contiguous runs
-    __shared__ uint32_t sval[RS_TILE];
-    __shared__ uint32_t wsum[RS_WARPS + 1];
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    for (int b = threadIdx.x; b < RS_WARPS * RS_BINS; b += RS_THREADS) (&cnt[0][0])[b] = 0;
-    __syncthreads();
-
-    // warp w owns the contiguous sub-tile [w*32*ITEMS, (w+1)*32*ITEMS), processed in ITEMS rounds of 32 (stable order)
-    const uint64_t wbase = (uint64_t) blockIdx.x * RS_TILE + (uint64_t) warp * (32 * RS_ITEMS);
-    uint64_t key[RS_ITEMS];
-    uint32_t rank[RS_ITEMS];
-    const uint32_t lt = (1u << lane) - 1u;
-#pragma unroll
-    for (int k = 0; k < RS_ITEMS; ++k) {
-        const uint64_t i = wbase + (uint64_t) k * 32 + lane;
-        const bool valid = i < n;
-        key[k] = valid ? keys_in[i] : ~0ull;
-        const uint32_t d = valid ? (uint32_t) ((key[k] >> shift) & 0xff) : 0x100u;  // invalid lanes never match a real digit
-        const uint32_t peers = __match_any_sync(0xffffffffu, d);
-        const int leader = __ffs(peers) - 1;
-        uint32_t prior = 0;
-        if (valid && lane == leader) {
-            prior = cnt[warp][d];
-            cnt[warp][d] = prior + __popc(peers);
-        }
-        prior = __shfl_sync(0xffffffffu, prior, leader);
-        rank[k] = prior + __popc(peers & lt);
-    }
-    __syncthreads();
-    // thread b owns digit b: exclusive prefix of the digit over the warps, then over the digits of the tile
-    uint32_t digit_total = 0;
-    {
-        const int b = threadIdx.x;
-#pragma unroll
-        for (int w = 0; w < RS_WARPS; ++w) {
-            const uint32_t c = cnt[w][b];
-            cnt[w][b] = digit_total;
-            digit_total += c;
-        }
-    }
-    uint32_t tile_total;
-    const uint32_t digit_start = block_excl_scan<RS_THREADS>(digit_total, &tile_total, wsum);
-    {
-        const int b = threadIdx.x;
-#pragma unroll
-        for (int w = 0; w < RS_WARPS; ++w) cnt[w][b] += digit_start;
-        gbase[b] = hist_scanned[(size_t) b * n_tiles + blockIdx.x] - digit_start;
-    }
-    __syncthreads();
-#pragma unroll
-    for (int k = 0; k < RS_ITEMS; ++k) {
-        const uint64_t i = wbase + (uint64_t) k * 32 + lane;
-        if (i < n) {
-            const uint32_t d = (uint32_t) ((key[k] >> shift) & 0xff);
-            const uint32_t pos = cnt[warp][d] + rank[k];
-            skey[pos] = key[k];
-            sval[pos] = IOTA_VALS ? (uint32_t) i : vals_in[i];
-        }
-    }
-    __syncthreads();
-    const uint64_t tile_base = (uint64_t) blockIdx.x * RS_TILE;
-    const uint32_t tile_count = (uint32_t) (n - tile_base < (uint64_t) RS_TILE ? n - tile_base : (uint64_t) RS_TILE);
-    for (uint32_t pos = threadIdx.x; pos < tile_count; pos += RS_THREADS) {
-        const uint64_t kk = skey[pos];
-        const uint32_t d = (uint32_t) ((kk >> shift) & 0xff);
-        const uint64_t g = (uint64_t) gbase[d] + pos;
-        keys_out[g] = kk;
-        vals_out[g] = sval[pos];
-    }
-}
-
-inline uint32_t rs_tiles_for(uint64_t n) { return (uint32_t) ((n + RS_TILE - 1) / RS_TILE); }
-// scratch requirement in uint32 elements: histogram table + scan tile sums
-inline size_t rs_scratch_elems(uint64_t n) {
-    const size_t hist = (size_t) RS_BINS * rs_tiles_for(n);
-    return hist + scan_tiles_for(hist) + 16;
-}
-
-// Sorts n (key, val) pairs on bits [0, key_bits).  vals_a == nullptr on input means "vals = 0..n-1".
-// Ping-pongs between (keys_a, vals_a) and (keys_b, vals_b); on return *keys_sorted / *vals_sorted point at the
-// buffers that hold the result.
-inline int radix_sort_pairs(nb_ctx *ctx, uint64_t *keys_a, uint32_t *vals_a, uint64_t *keys_b, uint32_t *vals_b,
-                            uint64_t n, int key_bits, uint32_t *scratch, uint64_t **keys_sorted,
-                            uint32_t **vals_sorted, bool iota_first) {
-    uint64_t *kin = keys_a, *kout = keys_b;
-    uint32_t *vin = vals_a, *vout = vals_b;
-    if (n == 0) { *keys_sorted = kin; *vals_sorted = vin; return NB_OK; }
-    const uint32_t tiles = rs_tiles_for(n);
-    const size_t hist_elems = (size_t) RS_BINS * tiles;
-    uint32_t *hist = scratch;
-    uint32_t *tile_tmp = scratch + hist_elems;
-    bool first = true;
-    for (int shift = 0; shift < key_bits; shift += 8) {
-        rs_hist_kernel<<<tiles, RS_THREADS, 0, ctx->stream>>>(kin, n, shift, tiles, hist);
-        NB_LAUNCH_CHECK(ctx);
-        NB_CHECK(exclusive_scan_u32(ctx, hist, hist, hist_elems, tile_tmp, nullptr));
-        if (first && iota_first)
-            rs_scatter_kernel<true><<<tiles, RS_THREADS, 0, ctx->stream>>>(kin, vin, n, shift, tiles, hist, kout, vout);
-        else
-            rs_scatter_kernel<false><<<tiles, RS_THREADS, 0, ctx->stream>>>(kin, vin, n, shift, tiles, hist, kout, vout);
-        NB_LAUNCH_CHECK(ctx);
-        first = false;
-        uint64_t *tk = kin; kin = kout; kout = tk;
-        uint32_t *tv = vin; vin = vout; vout = tv;
-    }
-    *keys_sorted = kin;
-    *vals_sorted = vin;
-    return NB_OK;
-}
-
+constexpr int RS_BINS = 256;                      // 8-bit digits
 
 // ---------------------------------------------------------------------------------------------------------------
-// One-sweep form of the same stable LSD sort (default).  The digit histograms of ALL passes are taken in one read of
+// Stable LSD radix sort, 8-bit digits, one-sweep form.  The digit histograms of ALL passes are taken in one read of
 // the keys before the first pass (a stable sort does not change them), so a pass is a single kernel: every tile
 // ranks its keys, publishes its per-digit counts and obtains the counts of the tiles before it by decoupled
 // look-back over a status table ({flag, count} packed in one 32-bit word per (tile, digit): 1 = the tile's own
 // count, 2 = inclusive prefix over tiles 0..t).  Tiles are numbered by an atomic ticket, so a tile only ever waits
-// for tiles that are already running.  Per pass this drops the per-tile histogram kernel (one more read of the
-// keys) and the three-kernel scan of the 256 x tiles table; the result is the same permutation bit for bit.
+// for tiles that are already running.  (Round 1 also carried a histogram / scan / scatter form with three kernels and
+// a 256 x tiles table scan per pass; it produced the same permutation bit for bit and was removed.)
 // ---------------------------------------------------------------------------------------------------------------
 constexpr int OS_MAX_PASSES = 8;
 constexpr uint32_t OS_FLAG_COUNT = 1u << 30, OS_FLAG_PREFIX = 2u << 30, OS_VALUE_MASK = (1u << 30) - 1u;
 
+// Packed sort word of the Barnes-Hut build: the 63-bit octant-path key in the upper bits, the body's storage slot in the
+// lower idx_bits (the lowest key bits are dropped; bodies that agree on all kept key bits are ordered afterwards by
+// their full keys).  idx_bits == 0: plain keys.
+__device__ __forceinline__ uint64_t os_pack(uint64_t key, uint64_t i, int idx_bits) {
+    if (idx_bits == 0) return key;
+    const uint64_t mask = (1ull << idx_bits) - 1ull;
+    return ((key << 1) & ~mask) | i;
+}
+
 // all-pass digit histograms; adjacent equal digits inside a warp are added as one run (the keys of the high passes are
-// nearly sorted from the previous step, so a warp usually holds one or two distinct high digits)
+// nearly sorted from the previous step, so a warp usually holds one or two distinct high digits).  Pass p looks at the
+// 8 bits from bit first_shift + 8 p.
 __global__ void __launch_bounds__(256)
-os_hist_kernel(const uint64_t *__restrict__ keys, uint64_t n, int passes, uint32_t *__restrict__ ghist /* [passes][256] */) {
+os_hist_kernel(const uint64_t *__restrict__ keys, uint64_t n, int passes, int first_shift, int idx_bits,
+               uint32_t *__restrict__ ghist /* [passes][256] */) {
     __shared__ uint32_t h[OS_MAX_PASSES][RS_BINS];
     for (int b = threadIdx.x; b < OS_MAX_PASSES * RS_BINS; b += blockDim.x) (&h[0][0])[b] = 0;
     __syncthreads();
@@ -287,7 +155,7 @@ os_hist_kernel(const uint64_t *__restrict__ keys, uint64_t n, int passes, uint32
 #pragma unroll
         for (int u = 0; u < U; ++u) {
             const uint64_t i = i0 + (uint64_t) u * stride;
-            key[u] = i < n ? keys[i] : 0;
+            key[u] = i < n ? os_pack(keys[i], i, idx_bits) : 0;
         }
 #pragma unroll
         for (int u = 0; u < U; ++u) {
@@ -295,7 +163,7 @@ os_hist_kernel(const uint64_t *__restrict__ keys, uint64_t n, int passes, uint32
             if (i >= n_round) break;                                      // warp-uniform
             const bool valid = i < n;
             for (int p = 0; p < passes; ++p) {
-                const uint32_t d = valid ? (uint32_t) ((key[u] >> (8 * p)) & 0xff) : 0x100u;
+                const uint32_t d = valid ? (uint32_t) ((key[u] >> (first_shift + 8 * p)) & 0xff) : 0x100u;
                 const uint32_t prev = __shfl_up_sync(0xffffffffu, d, 1);
                 const bool head = lane == 0 || d != prev;
                 const uint32_t heads = __ballot_sync(0xffffffffu, head);
@@ -326,18 +194,24 @@ os_scan_kernel(uint32_t *__restrict__ ghist, int passes) {
     }
 }
 
-template <int THREADS, int ITEMS, bool IOTA_VALS>
+// MODE: OS_PAIRS = (key, value) pairs; OS_PAIRS_IOTA = the same, values of the first pass are 0..n-1; OS_WORDS = 64-bit
+// words alone (no value arrays: the packed (key | slot) words of the Barnes-Hut build); OS_WORDS_PACK = the first pass
+// of a packed sort: reads the plain keys and packs the slot index into the low idx_bits on the fly.
+enum { OS_PAIRS = 0, OS_PAIRS_IOTA = 1, OS_WORDS = 2, OS_WORDS_PACK = 3 };
+
+template <int THREADS, int ITEMS, int MODE>
 __global__ void __launch_bounds__(THREADS, THREADS == 256 ? 5 : 4)
 os_scatter_kernel(const uint64_t *__restrict__ keys_in, const uint32_t *__restrict__ vals_in, uint64_t n, int shift,
                   const uint32_t *__restrict__ gstart /* [256] of this pass */, uint32_t *status /* [tiles][256] */,
-                  uint32_t *ticket, uint64_t *__restrict__ keys_out, uint32_t *__restrict__ vals_out) {
+                  uint32_t *ticket, uint64_t *__restrict__ keys_out, uint32_t *__restrict__ vals_out, int idx_bits) {
     constexpr int TILE = THREADS * ITEMS;
     constexpr int WARPS = THREADS / 32;
+    constexpr bool WORDS = MODE == OS_WORDS || MODE == OS_WORDS_PACK;
     static_assert(THREADS >= RS_BINS, "thread b owns digit b");
     extern __shared__ __align__(16) unsigned char os_smem[];
     uint64_t *skey = reinterpret_cast<uint64_t *>(os_smem);                       // TILE keys staged in digit order
-    uint32_t *sval = reinterpret_cast<uint32_t *>(skey + TILE);                   // TILE values
-    uint32_t(*cnt)[RS_BINS] = reinterpret_cast<uint32_t(*)[RS_BINS]>(sval + TILE);  // [WARPS][RS_BINS]
+    uint32_t *sval = reinterpret_cast<uint32_t *>(skey + TILE);                   // TILE values (pairs only)
+    uint32_t(*cnt)[RS_BINS] = reinterpret_cast<uint32_t(*)[RS_BINS]>(sval + (WORDS ? 0 : TILE));  // [WARPS][RS_BINS]
     uint32_t *gbase = &cnt[0][0] + WARPS * RS_BINS;                            // [RS_BINS]
     uint32_t *wsum = gbase + RS_BINS;                                             // [WARPS + 1]
     uint32_t *s_tile = wsum + WARPS + 1;
@@ -356,7 +230,7 @@ os_scatter_kernel(const uint64_t *__restrict__ keys_in, const uint32_t *__restri
 #pragma unroll
     for (int k = 0; k < ITEMS; ++k) {
         const uint64_t i = wbase + (uint64_t) k * 32 + lane;
-        key[k] = i < n ? keys_in[i] : ~0ull;
+        key[k] = i < n ? (MODE == OS_WORDS_PACK ? os_pack(keys_in[i], i, idx_bits) : keys_in[i]) : ~0ull;
     }
     // rank of a key among the keys of its warp with the same digit: the leader of each group of equal digits adds the
     // group size to the warp's counter with ONE shared-memory atomic that returns the count so far.  The ITEMS atomics
@@ -433,7 +307,7 @@ os_scatter_kernel(const uint64_t *__restrict__ keys_in, const uint32_t *__restri
             const uint32_t d = (uint32_t) ((key[k] >> shift) & 0xff);
             const uint32_t pos = cnt[warp][d] + rank[k];
             skey[pos] = key[k];
-            sval[pos] = IOTA_VALS ? (uint32_t) i : vals_in[i];
+            if (!WORDS) sval[pos] = MODE == OS_PAIRS_IOTA ? (uint32_t) i : vals_in[i];
         }
     }
     __syncthreads();
@@ -443,7 +317,7 @@ os_scatter_kernel(const uint64_t *__restrict__ keys_in, const uint32_t *__restri
         const uint32_t d = (uint32_t) ((kk >> shift) & 0xff);
         const uint64_t g = (uint64_t) gbase[d] + pos;
         keys_out[g] = kk;
-        vals_out[g] = sval[pos];
+        if (!WORDS) vals_out[g] = sval[pos];
     }
 }
 
@@ -460,8 +334,8 @@ inline uint32_t os_tiles_for(uint64_t n) { return (uint32_t) ((n + OS_THREADS * 
 inline size_t os_scratch_elems(uint64_t n) {
     return (size_t) OS_MAX_PASSES * RS_BINS + 64 + (size_t) OS_MAX_PASSES * os_tiles_for(n) * RS_BINS;
 }
-constexpr size_t os_smem_bytes(int threads, int items) {
-    return (size_t) threads * items * 12 + (size_t) ((threads / 32) * RS_BINS + RS_BINS + threads / 32 + 1 + 3) * 4;
+constexpr size_t os_smem_bytes(int threads, int items, bool words = false) {
+    return (size_t) threads * items * (words ? 8 : 12) + (size_t) ((threads / 32) * RS_BINS + RS_BINS + threads / 32 + 1 + 3) * 4;
 }
 
 // same contract as radix_sort_pairs
@@ -480,7 +354,7 @@ inline int onesweep_sort_pairs(nb_ctx *ctx, uint64_t *keys_a, uint32_t *vals_a, 
     NB_CUDA(ctx, cudaMemsetAsync(scratch, 0, ((size_t) OS_MAX_PASSES * RS_BINS + 64 + (size_t) passes * tiles * RS_BINS) * sizeof(uint32_t),
                                  ctx->stream));
     const unsigned hgrid = (unsigned) std::min<uint64_t>((n + 2047) / 2048, (uint64_t) ctx->sm_count * 8);
-    os_hist_kernel<<<hgrid, 256, 0, ctx->stream>>>(kin, n, passes, ghist);
+    os_hist_kernel<<<hgrid, 256, 0, ctx->stream>>>(kin, n, passes, 0, 0, ghist);
     NB_LAUNCH_CHECK(ctx);
     os_scan_kernel<<<1, RS_BINS, 0, ctx->stream>>>(ghist, passes);
     NB_LAUNCH_CHECK(ctx);
@@ -489,17 +363,56 @@ inline int onesweep_sort_pairs(nb_ctx *ctx, uint64_t *keys_a, uint32_t *vals_a, 
     for (int p = 0; p < passes; ++p) {
         uint32_t *st = status + (size_t) p * tiles * RS_BINS;
         if (p == 0 && iota_first)
-            os_scatter_kernel<OS_THREADS, OS_ITEMS, true><<<tiles, OS_THREADS, smem, ctx->stream>>>(kin, vin, n, 8 * p, ghist + p * RS_BINS, st,
-                                                                                                 tickets + p, kout, vout);
+            os_scatter_kernel<OS_THREADS, OS_ITEMS, OS_PAIRS_IOTA><<<tiles, OS_THREADS, smem, ctx->stream>>>(
+                kin, vin, n, 8 * p, ghist + p * RS_BINS, st, tickets + p, kout, vout, 0);
         else
-            os_scatter_kernel<OS_THREADS, OS_ITEMS, false><<<tiles, OS_THREADS, smem, ctx->stream>>>(kin, vin, n, 8 * p, ghist + p * RS_BINS, st,
-                                                                                                  tickets + p, kout, vout);
+            os_scatter_kernel<OS_THREADS, OS_ITEMS, OS_PAIRS><<<tiles, OS_THREADS, smem, ctx->stream>>>(
+                kin, vin, n, 8 * p, ghist + p * RS_BINS, st, tickets + p, kout, vout, 0);
         NB_LAUNCH_CHECK(ctx);
         uint64_t *tk = kin; kin = kout; kout = tk;
         uint32_t *tv = vin; vin = vout; vout = tv;
     }
     *keys_sorted = kin;
     *vals_sorted = vin;
+    return NB_OK;
+}
+
+// Packed form for the Barnes-Hut build: ONE 64-bit word per body, {upper bits of the 63-bit key | storage slot in the
+// low idx_bits}, sorted on its upper `passes` x 8 bits only.  A pass moves 16 B per body instead of 24 B, and 5 passes
+// (40 key bits = 13 octree levels) replace 8; bodies that agree on all sorted bits are put in order afterwards from
+// their full keys (bh_build.cu).  Sorting the words is sorting (key prefix, slot): stable by construction.
+// keys: plain keys (read by the first pass only); words_a / words_b: ping-pong buffers.  Returns the sorted words.
+inline int onesweep_sort_packed(nb_ctx *ctx, const uint64_t *keys, uint64_t *words_a, uint64_t *words_b, uint64_t n,
+                                int idx_bits, int passes, uint32_t *scratch, uint64_t **words_sorted) {
+    if (passes < 1 || passes > OS_MAX_PASSES) return nb_fail(ctx, NB_ERR_INVALID, "onesweep_sort_packed: bad pass count");
+    const int first_shift = 64 - 8 * passes;
+    const uint32_t tiles = os_tiles_for(n);
+    uint32_t *ghist = scratch;
+    uint32_t *tickets = scratch + (size_t) OS_MAX_PASSES * RS_BINS;
+    uint32_t *status = tickets + 64;
+    NB_CUDA(ctx, cudaMemsetAsync(scratch, 0, ((size_t) OS_MAX_PASSES * RS_BINS + 64 + (size_t) passes * tiles * RS_BINS) * sizeof(uint32_t),
+                                 ctx->stream));
+    const unsigned hgrid = (unsigned) std::min<uint64_t>((n + 2047) / 2048, (uint64_t) ctx->sm_count * 8);
+    os_hist_kernel<<<hgrid, 256, 0, ctx->stream>>>(keys, n, passes, first_shift, idx_bits, ghist);
+    NB_LAUNCH_CHECK(ctx);
+    os_scan_kernel<<<1, RS_BINS, 0, ctx->stream>>>(ghist, passes);
+    NB_LAUNCH_CHECK(ctx);
+    constexpr size_t smem = os_smem_bytes(OS_THREADS, OS_ITEMS, true);
+    const uint64_t *kin = keys;
+    uint64_t *kout = words_a;
+    for (int p = 0; p < passes; ++p) {
+        uint32_t *st = status + (size_t) p * tiles * RS_BINS;
+        if (p == 0)
+            os_scatter_kernel<OS_THREADS, OS_ITEMS, OS_WORDS_PACK><<<tiles, OS_THREADS, smem, ctx->stream>>>(
+                kin, nullptr, n, first_shift + 8 * p, ghist + p * RS_BINS, st, tickets + p, kout, nullptr, idx_bits);
+        else
+            os_scatter_kernel<OS_THREADS, OS_ITEMS, OS_WORDS><<<tiles, OS_THREADS, smem, ctx->stream>>>(
+                kin, nullptr, n, first_shift + 8 * p, ghist + p * RS_BINS, st, tickets + p, kout, nullptr, idx_bits);
+        NB_LAUNCH_CHECK(ctx);
+        kin = kout;
+        kout = kout == words_a ? words_b : words_a;
+    }
+    *words_sorted = const_cast<uint64_t *>(kin);
     return NB_OK;
 }
 

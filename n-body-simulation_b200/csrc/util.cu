@@ -76,7 +76,7 @@ extern "C" int nb_util_group_by_subtree(nb_ctx *ctx, uint32_t n, const uint32_t 
     NB_TRY(nb_alloc(ctx, &d_vb, (size_t) n));
     NB_TRY(nb_alloc(ctx, &d_ka, (size_t) n));
     NB_TRY(nb_alloc(ctx, &d_kb, (size_t) n));
-    NB_TRY(nb_alloc(ctx, &d_scratch, nbprim::rs_scratch_elems(n)));
+    NB_TRY(nb_alloc(ctx, &d_scratch, nbprim::os_scratch_elems(n)));
     NB_TRY_CUDA(cudaMemcpyAsync(d_sub, subtree_of_body, n * sizeof(uint32_t), cudaMemcpyHostToDevice, ctx->stream));
     NB_TRY_CUDA(cudaMemsetAsync(d_cnt, 0, node_count * sizeof(uint32_t), ctx->stream));
     const unsigned gb = (n + 255) / 256, gn = (node_count + 255) / 256;
@@ -92,7 +92,7 @@ extern "C" int nb_util_group_by_subtree(nb_ctx *ctx, uint32_t n, const uint32_t 
     ctx->launches++;
     uint64_t *ks = nullptr;
     uint32_t *vs = nullptr;
-    NB_TRY(nbprim::radix_sort_pairs(ctx, d_ka, d_va, d_kb, d_vb, n, 32, d_scratch, &ks, &vs, true));
+    NB_TRY(nbprim::onesweep_sort_pairs(ctx, d_ka, d_va, d_kb, d_vb, n, 32, d_scratch, &ks, &vs, true));
     uint32_t totals[2] = {0, 0};
     NB_TRY_CUDA(cudaMemcpyAsync(totals, d_total, sizeof totals, cudaMemcpyDeviceToHost, ctx->stream));
     NB_TRY_CUDA(cudaStreamSynchronize(ctx->stream));

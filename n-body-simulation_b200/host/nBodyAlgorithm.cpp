@@ -149,6 +149,8 @@ void nBodyAlgorithm::runTimeLoop(const SimulationData &d, const std::function<vo
             }
             if (run >= 6) {
                 check(nb_advance(ctx, batchAlgorithm, dt, run, ms), "nb_advance");
+                // a tree build that failed in the middle of the batch (node pool, coincident bodies) is reported here
+                check(nb_synchronize(ctx), "nb_advance (batch)");
                 for (unsigned k = 0; k < run; ++k) {
                     recordForceTimers(ms);
                     timer.addTimeToSequence("Leapfrog Part 1", ms[NB_T_LEAPFROG1]);
