@@ -206,6 +206,10 @@ const char *nb_timer_name(int timer);
 #define NB_COMM_ID_BYTES 128
 int nb_comm_get_unique_id(uint8_t id[NB_COMM_ID_BYTES]); /* rank 0 creates, host broadcasts               */
 int nb_comm_init(nb_ctx *ctx, const uint8_t id[NB_COMM_ID_BYTES], int world_size, int rank);
+/* 1 when every rank has mapped every other rank's state arrays (CUDA IPC over NVLink): the Barnes-Hut walk then stores
+ * its results straight into all ranks' arrays (two barriers instead of the all-gather) and nb_advance runs its fused
+ * form on several GPUs.  0: NCCL all-gather path (IPC unavailable, NB_DISABLE_P2P set, or more than 8 ranks).        */
+int nb_comm_p2p_enabled(const nb_ctx *ctx);
 /* slice of targets [begin, end) a rank owns (host-side logic; no GPU needed)                             */
 void nb_slice_bounds(uint64_t n, int world_size, int rank, uint64_t *begin, uint64_t *end);
 

@@ -52,7 +52,7 @@ EXPORTED_SYMBOLS = [
     "nb_op_naive_accelerations", "nb_op_barnes_hut_accelerations", "nb_bh_tree_info", "nb_bh_aabb",
     "nb_bh_export_canonical", "nb_bh_sorted_bodies", "nb_bh_enable_stats", "nb_bh_get_stats",
     "nb_util_group_by_subtree", "nb_enable_timers", "nb_get_timers", "nb_timer_name", "nb_comm_get_unique_id",
-    "nb_comm_init", "nb_slice_bounds", "nb_event_record", "nb_event_elapsed_ms", "nb_measure_fp64_peak", "nb_launch_count", "nb_device_pointers",
+    "nb_comm_init", "nb_comm_p2p_enabled", "nb_slice_bounds", "nb_event_record", "nb_event_elapsed_ms", "nb_measure_fp64_peak", "nb_launch_count", "nb_device_pointers",
 ]
 
 _lib = None
@@ -115,6 +115,7 @@ def load_library():
     L.nb_timer_name.restype = C.c_char_p
     L.nb_comm_get_unique_id.argtypes = [C.POINTER(C.c_uint8)]
     L.nb_comm_init.argtypes = [vp, C.POINTER(C.c_uint8), C.c_int, C.c_int]
+    L.nb_comm_p2p_enabled.argtypes = [vp]
     L.nb_slice_bounds.argtypes = [C.c_uint64, C.c_int, C.c_int, _u64p, _u64p]
     L.nb_slice_bounds.restype = None
     L.nb_event_record.argtypes = [vp, C.c_int]
@@ -384,3 +385,6 @@ class Context:
     def comm_init(self, unique_id, world_size, rank):
         buf = (C.c_uint8 * NB_COMM_ID_BYTES).from_buffer_copy(unique_id)
         self._ck(self.L.nb_comm_init(self.h, buf, world_size, rank))
+
+    def p2p_enabled(self):
+        return bool(self.L.nb_comm_p2p_enabled(self.h))

@@ -226,6 +226,8 @@ int nbk_comm_allreduce_sum(nb_ctx *ctx, double *buf, size_t count) {
     return NB_OK;
 }
 
+extern "C" int nb_comm_p2p_enabled(const nb_ctx *ctx) { return ctx && ctx->p2p_ok ? 1 : 0; }
+
 extern "C" void nb_slice_bounds(uint64_t n, int world_size, int rank, uint64_t *begin, uint64_t *end) {
     if (world_size < 1) world_size = 1;
     const uint64_t chunk = (n + world_size - 1) / world_size;

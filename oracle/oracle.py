@@ -41,6 +41,7 @@ def lib():
         L.orc_tree_create.argtypes = [C.c_uint32, C.c_uint32]
         L.orc_tree_destroy.argtypes = [C.c_void_p]
         L.orc_tree_build.argtypes = [C.c_void_p, _dp, _dp, _dp, _dp, C.c_int]
+        L.orc_tree_build_ordered.argtypes = [C.c_void_p, _dp, _dp, _dp, _dp, C.c_int, _up]
         L.orc_tree_num_nodes.restype = C.c_uint32
         L.orc_tree_num_nodes.argtypes = [C.c_void_p]
         L.orc_tree_max_depth.argtypes = [C.c_void_p]
@@ -54,6 +55,8 @@ def lib():
         L.orc_tree_canonical.argtypes = [C.c_void_p, _up, _u64p, _u64p, _up, _up, _up] + [_dp] * 8
         L.orc_bh_accel.argtypes = [C.c_void_p, _dp, _dp, _dp, C.c_double, C.c_double, C.c_double, C.c_int, _dp, _dp,
                                    _dp, _u64p, C.c_int]
+        L.orc_bh_accel_sample.argtypes = [C.c_void_p, _dp, _dp, _dp, C.c_double, C.c_double, C.c_double, C.c_uint32, _up,
+                                          _dp, _dp, _dp, _u64p, C.c_int]
         L.orc_naive_accel_rows.argtypes = [C.c_uint32, _dp, _dp, _dp, _dp, C.c_double, C.c_double, C.c_uint32,
                                            C.c_uint32, _dp, _dp, _dp, C.c_int]
         L.orc_leapfrog_part1.argtypes = [C.c_uint32, C.c_double] + [_dp] * 12
@@ -184,10 +187,30 @@ def sort_bodies_for_subtrees(subtree_of_body, counts, subtrees, n_subtrees):
     return start, sorted_bodies
 
 
+def morton_order(x, y, z, bits=20):
+    """Permutation that visits the bodies along a Z-order curve of a 2^bits grid (locality only: nothing depends on it)."""
+    def spread(v):
+        v = v.astype(np.uint64) & np.uint64(0x1fffff)
+        v = (v | (v << np.uint64(32))) & np.uint64(0x1f00000000ffff)
+        v = (v | (v << np.uint64(16))) & np.uint64(0x1f0000ff0000ff)
+        v = (v | (v << np.uint64(8))) & np.uint64(0x100f00f00f00f00f)
+        v = (v | (v << np.uint64(4))) & np.uint64(0x10c30c30c30c30c3)
+        v = (v | (v << np.uint64(2))) & np.uint64(0x1249249249249249)
+        return v
+    lo = min(x.min(), y.min(), z.min(), 0.0)
+    hi = max(x.max(), y.max(), z.max(), 0.0)
+    scale = ((1 << bits) - 1) / (hi - lo if hi > lo else 1.0)
+    q = [np.clip((a - lo) * scale, 0, (1 << bits) - 1).astype(np.uint64) for a in (x, y, z)]
+    code = spread(q[0]) | (spread(q[1]) << np.uint64(1)) | (spread(q[2]) << np.uint64(2))
+    return np.argsort(code, kind="stable").astype(np.uint32)
+
+
 class Tree:
     """BarnesHutOctree (canonical tree via sequential insertion) + its COM and in-order sort."""
 
-    def __init__(self, m, x, y, z, storage_param=16, aabb_work_items=1024):
+    def __init__(self, m, x, y, z, storage_param=16, aabb_work_items=1024, insertion_order=None):
+        """insertion_order: None (bodies 0..N-1), an explicit permutation, or "morton" (approximate Morton order computed
+        here: the canonical tree is the same for every order, a cache-friendly one builds large trees much faster)."""
         L = lib()
         self.m, self._pm = _d(m)
         self.x, self._px = _d(x)
@@ -196,7 +219,14 @@ class Tree:
         self.N = self.x.shape[0]
         self.S = storage_param * self.N
         self._h = C.c_void_p(L.orc_tree_create(self.N, self.S))
-        rc = L.orc_tree_build(self._h, self._px, self._py, self._pz, self._pm, aabb_work_items)
+        if insertion_order is None:
+            rc = L.orc_tree_build(self._h, self._px, self._py, self._pz, self._pm, aabb_work_items)
+        else:
+            if isinstance(insertion_order, str):
+                insertion_order = morton_order(self.x, self.y, self.z)
+            order, po = _u(insertion_order)
+            assert order.shape[0] == self.N
+            rc = L.orc_tree_build_ordered(self._h, self._px, self._py, self._pz, self._pm, aabb_work_items, po)
         if rc:
             raise RuntimeError("oracle tree build failed: %s" % {1: "node storage overflow", 2: "depth guard"}[rc])
         self.num_nodes = L.orc_tree_num_nodes(self._h)
@@ -257,6 +287,20 @@ class Tree:
         L.orc_bh_accel(self._h, self._px, self._py, self._pz, theta, eps2, G, int(sort_bodies),
                        ax.ctypes.data_as(_dp), ay.ctypes.data_as(_dp), az.ctypes.data_as(_dp),
                        st.ctypes.data_as(_u64p) if stats else None, nthreads)
+        return (ax, ay, az, st) if stats else (ax, ay, az)
+
+    def accel_sample(self, theta, ids, eps2=None, G=None, stats=False, nthreads=0):
+        """The same traversal for the sampled bodies `ids` only (outputs indexed by sample position)."""
+        L = lib()
+        eps2 = L.orc_epsilon2() if eps2 is None else eps2
+        G = L.orc_gravitational_constant() if G is None else G
+        ids, pids = _u(ids)
+        k = ids.shape[0]
+        ax = np.zeros(k); ay = np.zeros(k); az = np.zeros(k)
+        st = np.zeros((k, 5), dtype=np.uint64) if stats else None
+        L.orc_bh_accel_sample(self._h, self._px, self._py, self._pz, theta, eps2, G, k, pids, ax.ctypes.data_as(_dp),
+                              ay.ctypes.data_as(_dp), az.ctypes.data_as(_dp),
+                              st.ctypes.data_as(_u64p) if stats else None, nthreads)
         return (ax, ay, az, st) if stats else (ax, ay, az)
 
 

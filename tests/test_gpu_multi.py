@@ -1,6 +1,7 @@
-"""Two-rank run on real GPUs (skipped unless >= 2 GPUs are visible): accelerations computed by target-sharded ranks +
-NCCL all-gather must equal the single-GPU result (Barnes-Hut: bit for bit; naive: to 1e-13, its source-range
-segmentation depends on the slice size)."""
+"""Several ranks on real GPUs (each case skipped unless that many GPUs are visible): target-sharded ranks must reproduce
+the single-GPU result -- Barnes-Hut bit for bit (separate calls and the fused nb_advance, with the walk's peer stores
+over IPC-mapped memory and, with NB_DISABLE_P2P=1, with the NCCL all-gather), naive to 1e-13 (its source-range
+segmentation depends on the slice size), the sharded energy to 1e-12 -- for body counts that the ranks do not divide."""
 import os
 import subprocess
 import sys
@@ -24,40 +25,65 @@ def comm_id():
     ids = [nb.comm_unique_id() if rank == 0 else None]
     dist.broadcast_object_list(ids, src=0)
     return ids[0]
-n = 20001
-m, x, y, z, vx, vy, vz = nb.generators.plummer(n, seed=3)
-ref = nb.Context(device=rank, theta=0.5)
-ref.set_bodies(m, x, y, z, vx, vy, vz)
-ctx = nb.Context(device=rank, theta=0.5, world_size=world, rank=rank)
-ctx.comm_init(comm_id(), world, rank)
-ctx.set_bodies(m, x, y, z, vx, vy, vz)
-for c in (ref, ctx):
-    c.naive_accel()
-a, b = ref.accelerations(), ctx.accelerations()
-# the source range may be split into a different number of segments for a slice: rounding-level differences only
-assert all(np.allclose(u, v, rtol=1e-13, atol=0) for u, v in zip(a, b)), "naive sharded != single"
-for c in (ref, ctx):
-    c.bh_build(); c.bh_accel(); c.leapfrog_part1(0.01); c.bh_build(); c.bh_accel(); c.leapfrog_part2(0.01)
-a, b = ref.accelerations() + ref.positions() + ref.velocities(), ctx.accelerations() + ctx.positions() + ctx.velocities()
-assert all(np.array_equal(u, v) for u, v in zip(a, b)), "barnes-hut sharded != single"
-e1, e2 = ref.energy(), ctx.energy()
-assert np.all(np.abs(e1 - e2) <= 1e-12 * np.abs(e1)), (e1, e2)
+def same(u, v):
+    return all(np.array_equal(a, b) for a, b in zip(u, v))
+def state(c):
+    return c.positions() + c.velocities() + c.accelerations()
+want_p2p = os.environ.get("NB_DISABLE_P2P") is None
+for n, gen in ((20001, "plummer"), (700001, "uniform_sphere")):
+    m, x, y, z, vx, vy, vz = getattr(nb.generators, gen)(n, seed=3)
+    ref = nb.Context(device=rank, theta=0.5)
+    ref.set_bodies(m, x, y, z, vx, vy, vz)
+    ctx = nb.Context(device=rank, theta=0.5, world_size=world, rank=rank)
+    ctx.comm_init(comm_id(), world, rank)
+    ctx.set_bodies(m, x, y, z, vx, vy, vz)
+    assert ctx.p2p_enabled() == want_p2p, "peer mapping: %%s (expected %%s)" %% (ctx.p2p_enabled(), want_p2p)
+    if n < 100000:
+        for c in (ref, ctx):
+            c.naive_accel()
+        a, b = ref.accelerations(), ctx.accelerations()
+        # the source range may be split into a different number of segments for a slice: rounding-level differences only
+        assert all(np.allclose(u, v, rtol=1e-13, atol=0) for u, v in zip(a, b)), "naive sharded != single"
+        e1, e2 = ref.energy(), ctx.energy()
+        assert np.all(np.abs(e1 - e2) <= 1e-12 * np.abs(e1)), (e1, e2)
+    # separate calls
+    for c in (ref, ctx):
+        c.bh_build(); c.bh_accel(); c.leapfrog_part1(0.01); c.bh_build(); c.bh_accel(); c.leapfrog_part2(0.01)
+    assert same(state(ref), state(ctx)), "barnes-hut sharded != single (separate calls, n=%%d)" %% n
+    # batches of steps: fused walk + integrator, results stored into every rank's arrays by the walk itself
+    for k in (1, 2, 5):
+        ref.advance("BarnesHut", 0.01, k); ctx.advance("BarnesHut", 0.01, k)
+        assert same(state(ref), state(ctx)), "barnes-hut sharded != single (nb_advance %%d, n=%%d)" %% (k, n)
+    # and separate calls again on the state the batches left behind
+    for c in (ref, ctx):
+        c.leapfrog_part1(0.01); c.bh_build(); c.bh_accel(); c.leapfrog_part2(0.01)
+    assert same(state(ref), state(ctx)), "barnes-hut sharded != single (after the batches, n=%%d)" %% n
+    if n < 100000:
+        e1, e2 = ref.energy(), ctx.energy()
+        assert np.all(np.abs(e1 - e2) <= 1e-12 * np.abs(e1)), (e1, e2)
+    dist.barrier()
+    ctx.close(); ref.close()
 dist.barrier()
 if rank == 0:
-    print("MULTI_OK")
+    print("MULTI_OK p2p=%%s world=%%d" %% (want_p2p, world))
 dist.destroy_process_group()
 '''
 
 
-def test_two_ranks_match_single_gpu(tmp_path):
+@pytest.mark.parametrize("p2p", [True, False])
+@pytest.mark.parametrize("world", [2, 4, 8])
+def test_ranks_match_single_gpu(tmp_path, world, p2p):
     import torch
-    if torch.cuda.device_count() < 2:
-        pytest.skip("needs 2 GPUs")
+    if torch.cuda.device_count() < world:
+        pytest.skip("needs %d GPUs" % world)
     script = tmp_path / "worker.py"
     script.write_text(WORKER % ROOT)
-    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2",
-                        "--master-addr", "127.0.0.1", "--master-port", "29533", str(script)],
-                       capture_output=True, text=True, timeout=600)
+    env = dict(os.environ)
+    if not p2p:
+        env["NB_DISABLE_P2P"] = "1"
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(world),
+                        "--master-addr", "127.0.0.1", "--master-port", str(29533 + world + (0 if p2p else 10)), str(script)],
+                       capture_output=True, text=True, timeout=900, env=env)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-4000:]
     assert "MULTI_OK" in r.stdout
 
