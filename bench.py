@@ -270,7 +270,7 @@ def walk_roofline(visits, accepts, bodies_share, t_walk_s, sm_count, sm_mhz, n, 
     lane_ops = (BH_DP_PER_ACCEPT * accepts + BH_DP_PER_OPEN * opens) * bodies_share
     peak = sm_count * FP64_LANES_PER_SM * sm_mhz * 1e6 / 1e9            # G lane-ops/s
     achieved = lane_ops / t_walk_s / 1e9 if t_walk_s > 0 else 0.0
-    alg_bytes = (BH_BYTES_PER_VISIT * visits + BH_BYTES_PER_BODY * n) * bodies_share
+    alg_bytes = (BH_BYTES_PER_VISIT * visits + BH_BYTES_PER_BODY) * bodies_share
     return {"bound": "fp64", "kernel": "bh_traverse_iw_kernel", "achieved": achieved, "peak": peak,
             "unit": "G fp64 lane-ops/s", "frac": achieved / peak if peak else None,
             "traffic": NCU_TRAFFIC_BYTES.get(("bh", n)) if world == 1 else None,

@@ -65,6 +65,16 @@ typedef struct nb_config {
     int32_t precise_rsqrt;       /* 1 (default): cubic rsqrt refinement (~1 ulp); 0: linear (~2e-12 rel)   */
     int32_t world_size;          /* ranks sharing the bodies (1 = single GPU)                              */
     int32_t rank;                /* this context's rank                                                    */
+    /* Tuning and A/B switches (0 = production default everywhere; the Python binding names them as given here):
+     *   [0] ipt               naive: target bodies per consumer thread (register blocking); 0 -> 4
+     *   [1] unfused_advance   1: nb_advance keeps separate integrator kernels for Barnes-Hut (default: fused into the walk)
+     *   [2] naive_variant     naive: one of the {IPT, unroll, min CTAs per SM} instantiations swept in naive.cu
+     *   [3] walk_variant      Barnes-Hut walk: 20 grid-mapped, 50 persistent (SM-local tile queues), 51 persistent with
+     *                         CTA-synchronous tile rounds (experiment); 0 picks 50 from 2^19 bodies per call, else 20
+     *   [4] naive_segments    naive: number of source segments per target tile (0: chosen from the grid size)
+     *   [5] (unused)
+     *   [6] sort_variant      tree build: 1 full 8-pass (key, slot) sort, 2 packed 5-pass sort; 0: per build (see bh_build.cu)
+     *   [7] com_variant       centre of mass: 1 one launch per level instead of one cooperative launch              */
     int32_t reserved[8];
 } nb_config;
 
@@ -98,7 +108,9 @@ uint64_t nb_num_bodies(const nb_ctx *ctx);
 
 /* ---- force operators ---------------------------------------------------------------------------------- */
 /* NaiveAlgorithm::computeAccelerations_opt_{0,1,2} (NaiveAlgorithm.hpp:31-53, .cpp:262-482):
- * a_i = G * sum_j m_j r_ij (|r_ij|^2 + eps2)^(-3/2), j ascending, self term included.
+ * a_i = G * sum_j m_j r_ij (|r_ij|^2 + eps2)^(-3/2), self term included; j ascending inside up to 32 source segments
+ * whose partial sums are added in ascending order (the segment count depends on N only: the bits of the result do not
+ * depend on the device or on world_size).
  * With world_size > 1 the rank computes its target slice and all-gathers the accelerations.            */
 int nb_naive_accel(nb_ctx *ctx);
 

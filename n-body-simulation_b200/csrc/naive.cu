@@ -15,8 +15,10 @@
 //     s = m*d2^(-3/2) = y3 * (m + e*(1.5m + 1.875m*e))   [Taylor of (1-e)^(-3/2), |e| <~ 2^-20 -> error ~2e-18]
 //     = 6 DP ops including the mass multiply, then 3 DFMA accumulate: 15 DP instructions for the 21 algorithmic flops
 //     (SURVEY 8d).  precise_rsqrt=0 drops the quadratic term (14 DP ops, ~2e-12 relative).
-//   * summation order per target is j ascending exactly as the reference; the only differences to the oracle are the
-//     rsqrt refinement and FMA contraction (~1e-16 relative per term).
+//   * summation order per target: j ascending inside a source segment, segment partials added in ascending order.  Up to
+//     2^24 bodies the source range is cut into up to 32 segments (a function of N only, see launch_naive) so that a
+//     rank's slice of an 8-GPU run still fills the machine; the reference adds all j in one chain.  The differences to
+//     the oracle are this blocking, the rsqrt refinement and FMA contraction (~1e-16 relative per term).
 #include "common.cuh"
 
 #define NB_NAIVE_CONSUMER_WARPS 4
@@ -227,11 +229,15 @@ int launch_naive(nb_ctx *ctx, uint32_t n_tiles, uint32_t tile_len, uint64_t i_be
     const uint64_t grid = (count + per_cta - 1) / per_cta;
     const size_t smem = 128 + (size_t) NB_NAIVE_STAGES * tile_len * sizeof(nb_src_rec);
     // work quanta: aim for >= 32 CTAs per SM so the tail of the last wave is a few percent; split the source range
-    // into segments when there are too few target tiles (small N, or a rank's slice on many GPUs)
+    // into segments when there are too few target tiles (small N, or a rank's slice on many GPUs).  The number of
+    // segments fixes the summation order of a target (segment partials are added in ascending order), so it is a
+    // function of N alone -- sized for a rank's slice of an 8-GPU run of a 148-SM part, whatever this launch is: one
+    // GPU and eight produce the same bits, on any device.
     uint32_t segments = 1;
-    const uint64_t want = (uint64_t) ctx->sm_count * 32;
+    const uint64_t grid_full = (ctx->n + per_cta - 1) / per_cta;
+    const uint64_t want = (uint64_t) NB_SM_COUNT_FALLBACK * 32 * NB_MAX_PEERS;
     if (ctx->cfg.reserved[4] > 0) segments = (uint32_t) ctx->cfg.reserved[4];
-    else if (grid < want) segments = (uint32_t) ((want + grid - 1) / grid);
+    else if (grid_full < want) segments = (uint32_t) ((want + grid_full - 1) / grid_full);
     if (segments > 32) segments = 32;
     if (segments > n_tiles) segments = n_tiles;
     uint32_t seg_tiles = (n_tiles + segments - 1) / segments;

@@ -2,7 +2,11 @@
 
 #include "StateFile.hpp"
 
+#include <fcntl.h>
+#include <sys/stat.h>
 #include <unistd.h>
+
+#include <cctype>
 
 #include <algorithm>
 #include <chrono>
@@ -34,11 +38,59 @@ void nBodyAlgorithm::check(int status, const char *what) {
 }
 
 namespace {
-// single-node rendezvous for the NCCL unique id: rank 0 writes it to a file, the other ranks wait for it
+// Single-node rendezvous for the NCCL unique id: rank 0 writes it to a file, the other ranks wait for it.  The file
+// name carries the user id and a per-run nonce (the launcher's run id, else the launcher's pid: all ranks of one
+// torchrun share it), the file is created exclusively without following links (mode 0600) and its header repeats the
+// nonce, so a file left behind by a crashed run or planted by somebody else is never taken for this run's id.
+std::string runNonce() {
+    if (const char *p = std::getenv("TORCHELASTIC_RUN_ID")) return p;
+    return std::to_string((long) getppid());
+}
 std::string commFilePath() {
     if (const char *p = std::getenv("NBODY_COMM_FILE")) return p;
     const char *port = std::getenv("MASTER_PORT");
-    return std::string("/tmp/nbody_b200_nccl_") + (port ? port : "0") + ".id";
+    const char *dir = std::getenv("XDG_RUNTIME_DIR");
+    std::string nonce = runNonce();
+    for (char &c : nonce)
+        if (!std::isalnum((unsigned char) c)) c = '_';
+    return std::string(dir && *dir ? dir : "/tmp") + "/nbody_b200_nccl_" + std::to_string((long) getuid()) + "_" +
+           (port ? port : "0") + "_" + nonce + ".id";
+}
+struct CommFileRecord {
+    char magic[8];
+    char nonce[56];
+    uint8_t id[NB_COMM_ID_BYTES];
+};
+void fillHeader(CommFileRecord &r) {
+    std::memset(&r, 0, sizeof r);
+    std::memcpy(r.magic, "NBCOMM1", 8);
+    std::strncpy(r.nonce, runNonce().c_str(), sizeof r.nonce - 1);
+}
+void writeCommFile(const std::string &path, const uint8_t *id) {
+    CommFileRecord r;
+    fillHeader(r);
+    std::memcpy(r.id, id, NB_COMM_ID_BYTES);
+    const std::string tmp = path + ".tmp";
+    ::unlink(path.c_str());   // nobody waits yet for THIS run's file: anything here is stale
+    ::unlink(tmp.c_str());
+    const int fd = ::open(tmp.c_str(), O_WRONLY | O_CREAT | O_EXCL | O_NOFOLLOW, 0600);
+    if (fd < 0) throw std::runtime_error("cannot create " + tmp);
+    const bool ok = ::write(fd, &r, sizeof r) == (ssize_t) sizeof r;
+    ::close(fd);
+    if (!ok || ::rename(tmp.c_str(), path.c_str()) != 0) throw std::runtime_error("cannot write " + path);
+}
+bool readCommFile(const std::string &path, uint8_t *id) {
+    const int fd = ::open(path.c_str(), O_RDONLY | O_NOFOLLOW);
+    if (fd < 0) return false;
+    struct stat st;
+    CommFileRecord r, want;
+    fillHeader(want);
+    const bool ok = ::fstat(fd, &st) == 0 && st.st_uid == getuid() && S_ISREG(st.st_mode) &&
+                    ::read(fd, &r, sizeof r) == (ssize_t) sizeof r && std::memcmp(r.magic, want.magic, 8) == 0 &&
+                    std::memcmp(r.nonce, want.nonce, sizeof r.nonce) == 0;
+    ::close(fd);
+    if (ok) std::memcpy(id, r.id, NB_COMM_ID_BYTES);
+    return ok;
 }
 }  // namespace
 
@@ -52,15 +104,12 @@ void nBodyAlgorithm::openDevice(const SimulationData &d) {
         const std::string path = commFilePath();
         if (configuration::rank == 0) {
             check(nb_comm_get_unique_id(id), "nb_comm_get_unique_id");
-            const std::string tmp = path + ".tmp";
-            std::ofstream(tmp, std::ios::binary).write(reinterpret_cast<const char *>(id), sizeof id);
-            std::filesystem::rename(tmp, path);
+            writeCommFile(path, id);
         } else {
-            for (int tries = 0; !std::filesystem::exists(path); ++tries) {
+            for (int tries = 0; !readCommFile(path, id); ++tries) {
                 if (tries > 6000) throw std::runtime_error("timed out waiting for " + path);
                 std::this_thread::sleep_for(std::chrono::milliseconds(10));
             }
-            std::ifstream(path, std::ios::binary).read(reinterpret_cast<char *>(id), sizeof id);
         }
         check(nb_comm_init(ctx, id, configuration::worldSize, configuration::rank), "nb_comm_init");
         if (configuration::rank == 0) std::filesystem::remove(path);
