@@ -68,9 +68,9 @@ typedef struct nb_config {
     /* Tuning and A/B switches (0 = production default everywhere; the Python binding names them as given here):
      *   [0] ipt               naive: target bodies per consumer thread (register blocking); 0 -> 4
      *   [1] unfused_advance   1: nb_advance keeps separate integrator kernels for Barnes-Hut (default: fused into the walk)
-     *   [2] naive_variant     naive: one of the {IPT, unroll, min CTAs per SM} instantiations swept in naive.cu
-     *   [3] walk_variant      Barnes-Hut walk: 20 grid-mapped, 50 persistent (SM-local tile queues), 51 persistent with
-     *                         CTA-synchronous tile rounds (experiment); 0 picks 50 from 2^19 bodies per call, else 20
+     *   [2] naive_variant     naive: 1 round-1 form with a producer warp, 2 / 3 three / four CTAs per SM (A/B, see naive.cu)
+     *   [3] walk_variant      Barnes-Hut walk: 20 grid-mapped, 50 persistent (SM-local tile queues); 0 picks 50 from 2^19
+     *                         bodies per call, else 20
      *   [4] naive_segments    naive: number of source segments per target tile (0: chosen from the grid size)
      *   [5] (unused)
      *   [6] sort_variant      tree build: 1 full 8-pass (key, slot) sort, 2 packed 5-pass sort; 0: per build (see bh_build.cu)

@@ -277,29 +277,45 @@ __device__ __forceinline__ bool share_prefix(uint64_t hi_a, uint64_t lo_a, uint6
     if (d <= 21) return ((hi_a ^ hi_b) >> (63 - 3 * d)) == 0;
     return hi_a == hi_b && ((lo_a ^ lo_b) >> (63 - 3 * (d - 21))) == 0;
 }
+// the same for sorted body j against the key (hi_i, lo_i): the lower key word of j is only loaded when the question
+// reaches below level 21 (the searches of emit_kernel are dependent loads; nearly all of them stop at the upper word)
+__device__ __forceinline__ bool shares_prefix_with(const uint64_t *__restrict__ hi, const uint64_t *__restrict__ lo, uint64_t j,
+                                                   uint64_t hi_i, uint64_t lo_i, int d) {
+    const uint64_t hj = hi[j];
+    if (d <= 21) return ((hj ^ hi_i) >> (63 - 3 * d)) == 0;
+    return hj == hi_i && ((lo[j] ^ lo_i) >> (63 - 3 * (d - 21))) == 0;
+}
 
 __device__ __forceinline__ uint32_t digit_at(uint64_t hi, uint64_t lo, int level) {
     return level < 21 ? (uint32_t) ((hi >> (60 - 3 * level)) & 7) : (uint32_t) ((lo >> (60 - 3 * (level - 21))) & 7);
 }
 
-// ---- 3b. neighbour prefix lengths and per-body internal-node counts -----------------------------------------------------
+// ---- 3b. neighbour prefix lengths, per-body internal-node counts, per-depth node counts ----------------------------------
+// level[0..63] += internal nodes per depth (the sizes of the dense per-depth work lists of the centre-of-mass pass)
 __global__ void __launch_bounds__(256)
 delta_kernel(const uint64_t *__restrict__ hi, const uint64_t *__restrict__ lo, uint64_t n, int32_t *__restrict__ delta,
-             uint32_t *__restrict__ cnt, uint32_t *__restrict__ flags) {
+             uint32_t *__restrict__ cnt, uint32_t *__restrict__ flags, uint32_t *__restrict__ level) {
+    __shared__ uint32_t lcnt[NB_LEVELS];
+    __shared__ int smax;
+    if (threadIdx.x < NB_LEVELS) lcnt[threadIdx.x] = 0;
+    if (threadIdx.x == 0) smax = -1;
+    __syncthreads();
     const uint64_t i = (uint64_t) blockIdx.x * blockDim.x + threadIdx.x;
     int d_cur = -1;
     if (i < n) {
-        const uint64_t h = hi[i], l = lo[i];
-        const int d_prev = i > 0 ? common_digits(hi[i - 1], lo[i - 1], h, l) : -1;
-        d_cur = i + 1 < n ? common_digits(h, l, hi[i + 1], lo[i + 1]) : -1;
+        // the lower key words matter only between bodies that agree on the whole upper word
+        const uint64_t h = hi[i];
+        const uint64_t hp = i > 0 ? hi[i - 1] : 0, hn = i + 1 < n ? hi[i + 1] : 0;
+        const bool tie_p = i > 0 && hp == h, tie_n = i + 1 < n && hn == h;
+        const uint64_t l = (tie_p || tie_n) ? lo[i] : 0;
+        const int d_prev = i > 0 ? common_digits(hp, tie_p ? lo[i - 1] : 0, h, l) : -1;
+        d_cur = i + 1 < n ? common_digits(h, l, hn, tie_n ? lo[i + 1] : 0) : -1;
         delta[i] = d_cur;
         cnt[i] = d_cur > d_prev ? (uint32_t) (d_cur - d_prev) : 0u;
         if (d_cur >= NB_MAX_TREE_DEPTH) atomicOr(&flags[0], NB_FLAG_DEPTH);
+        for (int d = d_prev + 1; d <= d_cur && d < NB_LEVELS; ++d) atomicAdd(&lcnt[d], 1u);
     }
     // max depth of the tree = deepest leaf = max(delta) + 1: one atomic per block, and only when it raises the value
-    __shared__ int smax;
-    if (threadIdx.x == 0) smax = -1;
-    __syncthreads();
     int mx = d_cur;
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) mx = max(mx, __shfl_xor_sync(0xffffffffu, mx, o));
@@ -307,6 +323,7 @@ delta_kernel(const uint64_t *__restrict__ hi, const uint64_t *__restrict__ lo, u
     __syncthreads();
     if (threadIdx.x == 0 && smax >= 0 && (uint32_t) (smax + 1) > *(volatile uint32_t *) &flags[2])
         atomicMax(&flags[2], (uint32_t) (smax + 1));
+    if (threadIdx.x < NB_LEVELS && lcnt[threadIdx.x]) atomicAdd(&level[threadIdx.x], lcnt[threadIdx.x]);
 }
 
 // ---- 4. node emission ---------------------------------------------------------------------------------------------------
@@ -335,10 +352,10 @@ emit_kernel(const uint64_t *__restrict__ hi, const uint64_t *__restrict__ lo, co
     for (int k = (int) c - 1; k >= 0; --k) {
         const int d = d_prev + 1 + k;
         uint64_t step = 1;
-        while (r + step < n && share_prefix(hi[r + step], lo[r + step], hi_i, lo_i, d)) { r += step; step <<= 1; }
+        while (r + step < n && shares_prefix_with(hi, lo, r + step, hi_i, lo_i, d)) { r += step; step <<= 1; }
         while (step > 1) {
             step >>= 1;
-            if (r + step < n && share_prefix(hi[r + step], lo[r + step], hi_i, lo_i, d)) r += step;
+            if (r + step < n && shares_prefix_with(hi, lo, r + step, hi_i, lo_i, d)) r += step;
         }
         const uint64_t node = head + k;
         const uint64_t skip = r + 1 < n ? (r + 1) + base[r + 1] : M;
@@ -354,22 +371,8 @@ emit_kernel(const uint64_t *__restrict__ hi, const uint64_t *__restrict__ lo, co
 }
 
 // ---- 4b. per-depth lists of internal nodes (dense work lists for the centre-of-mass levels) ---------------------------------
-// level[0..63] = node count per depth, level[64..127] = start of the depth's segment in `list`, level[128..191] = fill cursor
-__global__ void __launch_bounds__(256)
-level_count_kernel(const int32_t *__restrict__ delta, uint64_t n, uint32_t *__restrict__ level) {
-    __shared__ uint32_t cnt[NB_LEVELS];
-    if (threadIdx.x < NB_LEVELS) cnt[threadIdx.x] = 0;
-    __syncthreads();
-    const uint64_t i = (uint64_t) blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n) {
-        const int d_prev = i > 0 ? delta[i - 1] : -1;
-        const int d_cur = delta[i];
-        for (int d = d_prev + 1; d <= d_cur; ++d) atomicAdd(&cnt[d], 1u);
-    }
-    __syncthreads();
-    if (threadIdx.x < NB_LEVELS && cnt[threadIdx.x]) atomicAdd(&level[threadIdx.x], cnt[threadIdx.x]);
-}
-
+// level[0..63] = node count per depth (delta_kernel), level[64..127] = start of the depth's segment in `list`,
+// level[128..191] = fill cursor
 __global__ void level_scan_kernel(uint32_t *__restrict__ level) {
     if (threadIdx.x == 0) {
         uint32_t run = 0;
@@ -444,45 +447,69 @@ com_leaf_kernel(uint64_t n, uint32_t *flags_in, const double *__restrict__ px,
 
 // One level of the bottom-up pass: internal node = sum over its children in octant order 0..7 (BarnesHutOctree.cpp:299-317).
 // `tid` / `nthreads`: this thread's index in, and the size of, the set of threads that share the level.
+// sum of the children of one node in octant order (octant code o = 4u + 2r + b  <->  visit rank 4u + 2b + (1-r):
+// octants 0..7 are ranks 1,3,0,2,5,7,4,6); an empty octant adds 0.0 in the reference: a no-op
+template <bool COHERENT>
+__device__ __forceinline__ void com_sum_and_store(const uint32_t (&child)[8], uint32_t p, double *com, double *msum4) {
+    const int rank_of_octant[8] = {1, 3, 0, 2, 5, 7, 4, 6};
+    double sumMasses = 0, cx = 0, cy = 0, cz = 0;
+#pragma unroll
+    for (int o = 0; o < 8; ++o) {
+        const uint32_t c = child[rank_of_octant[o]];
+        if (c != NB_NONE) {
+            const double2 *s2 = reinterpret_cast<const double2 *>(msum4 + 4 * (size_t) c);
+            // COHERENT: the sums of the level below were written by other CTAs of the SAME launch; read them from L2
+            const double2 a = COHERENT ? __ldcg(s2) : s2[0], b = COHERENT ? __ldcg(s2 + 1) : s2[1];
+            cx = __dadd_rn(cx, a.x);
+            cy = __dadd_rn(cy, a.y);
+            cz = __dadd_rn(cz, b.x);
+            sumMasses = __dadd_rn(sumMasses, b.y);
+        }
+    }
+    store_node(com, msum4, p, cx, cy, cz, sumMasses);
+}
+
+// A thread works on TWO nodes of the level at a time: finding a node's children is a chain of dependent loads along the
+// skip links (child k+1 = skip[child k], up to 8 hops), and the pass is bound by that latency (round 1, ncu: 77 cycles of
+// long-scoreboard stall per issue, DRAM 41 % active); two interleaved chains per thread double the loads in flight.
 template <bool COHERENT>
 __device__ __forceinline__ void com_level(int depth, const uint32_t *__restrict__ level, const uint32_t *__restrict__ list,
                                           const uint2 *__restrict__ meta, double *com, double *msum4,
                                           uint32_t tid, uint32_t nthreads) {
     const uint32_t count = level[depth];
     const uint32_t *nodes = list + level[NB_LEVELS + depth];
-    for (uint32_t k = tid; k < count; k += nthreads) {
-        const uint32_t p = nodes[k];
-        const uint32_t end = meta[p].x;
+    for (uint32_t k = tid; k < count; k += 2 * nthreads) {
+        const uint32_t k2 = k + nthreads;
+        const bool two = k2 < count;
+        const uint32_t pa = nodes[k], pb = two ? nodes[k2] : pa;
+        const uint32_t enda = meta[pa].x, endb = two ? meta[pb].x : 0u;
         // children (leaves, or depth+1 nodes finished before this level), indexed by their visit rank
-        uint32_t child[8];
+        uint32_t ca[8], cb[8];
 #pragma unroll
-        for (int r = 0; r < 8; ++r) child[r] = NB_NONE;
-        uint32_t ch = p + 1;
-        while (ch < end) {
-            const uint2 mc = meta[ch];
-            const uint32_t rank = nb_meta_rank(mc.y);
+        for (int r = 0; r < 8; ++r) ca[r] = cb[r] = NB_NONE;
+        uint32_t cha = pa + 1, chb = two ? pb + 1 : 0u;
+        while (cha < enda || chb < endb) {
+            const bool ga = cha < enda, gb = chb < endb;
+            uint2 ma = make_uint2(0u, 0u), mb = make_uint2(0u, 0u);
+            if (ga) ma = meta[cha];
+            if (gb) mb = meta[chb];
+            if (ga) {
+                const uint32_t rank = nb_meta_rank(ma.y);
 #pragma unroll
-            for (int r = 0; r < 8; ++r)
-                if (rank == (uint32_t) r) child[r] = ch;
-            ch = mc.x > ch ? mc.x : end;  // skip links always point forward
-        }
-        // octant code o = 4u + 2r + b  <->  visit rank 4u + 2b + (1-r):  octants 0..7 are ranks 1,3,0,2,5,7,4,6
-        const int rank_of_octant[8] = {1, 3, 0, 2, 5, 7, 4, 6};
-        double sumMasses = 0, cx = 0, cy = 0, cz = 0;
+                for (int r = 0; r < 8; ++r)
+                    if (rank == (uint32_t) r) ca[r] = cha;
+                cha = ma.x > cha ? ma.x : enda;  // skip links always point forward
+            }
+            if (gb) {
+                const uint32_t rank = nb_meta_rank(mb.y);
 #pragma unroll
-        for (int o = 0; o < 8; ++o) {
-            const uint32_t c = child[rank_of_octant[o]];
-            if (c != NB_NONE) {  // an empty octant adds 0.0 in the reference: a no-op
-                const double2 *s2 = reinterpret_cast<const double2 *>(msum4 + 4 * (size_t) c);
-                // COHERENT: the sums of the level below were written by other CTAs of the SAME launch; read them from L2
-                const double2 a = COHERENT ? __ldcg(s2) : s2[0], b = COHERENT ? __ldcg(s2 + 1) : s2[1];
-                cx = __dadd_rn(cx, a.x);
-                cy = __dadd_rn(cy, a.y);
-                cz = __dadd_rn(cz, b.x);
-                sumMasses = __dadd_rn(sumMasses, b.y);
+                for (int r = 0; r < 8; ++r)
+                    if (rank == (uint32_t) r) cb[r] = chb;
+                chb = mb.x > chb ? mb.x : endb;
             }
         }
-        store_node(com, msum4, p, cx, cy, cz, sumMasses);
+        com_sum_and_store<COHERENT>(ca, pa, com, msum4);
+        if (two) com_sum_and_store<COHERENT>(cb, pb, com, msum4);
     }
 }
 
@@ -676,7 +703,8 @@ int nbk_bh_build(nb_ctx *ctx) {
     const uint64_t *hi = b.key_hi, *lo = b.key_hi_alt;
     {
         nb_timer_scope t(ctx, NB_T_BUILD);
-        delta_kernel<<<g256, 256, 0, ctx->stream>>>(hi, lo, n, b.delta, b.chain_cnt, b.dev_flags);
+        NB_CUDA(ctx, cudaMemsetAsync(b.level, 0, 3 * NB_LEVELS * sizeof(uint32_t), ctx->stream));
+        delta_kernel<<<g256, 256, 0, ctx->stream>>>(hi, lo, n, b.delta, b.chain_cnt, b.dev_flags, b.level);
         NB_LAUNCH_CHECK(ctx);
         uint32_t *tile_tmp = b.hist;  // scan scratch (sort is finished)
         NB_CHECK(nbprim::exclusive_scan_u32(ctx, b.chain_cnt, b.chain_base, n, tile_tmp, b.dev_flags + 1));
@@ -684,9 +712,6 @@ int nbk_bh_build(nb_ctx *ctx) {
                                                    b.body_count, b.leaf_node);
         NB_LAUNCH_CHECK(ctx);
         // dense per-depth node lists for the centre-of-mass levels
-        NB_CUDA(ctx, cudaMemsetAsync(b.level, 0, 3 * NB_LEVELS * sizeof(uint32_t), ctx->stream));
-        level_count_kernel<<<g256, 256, 0, ctx->stream>>>(b.delta, n, b.level);
-        NB_LAUNCH_CHECK(ctx);
         level_scan_kernel<<<1, 32, 0, ctx->stream>>>(b.level);
         NB_LAUNCH_CHECK(ctx);
         level_fill_kernel<<<g256, 256, 0, ctx->stream>>>(b.delta, b.chain_base, n, b.dev_flags, b.level, b.level_list);

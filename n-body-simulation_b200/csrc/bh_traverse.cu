@@ -125,7 +125,7 @@ __device__ __noinline__ void walk_epilogue(const nb_walk_out &out, uint64_t b, d
     if (out.peers.world > 1) __threadfence_system();   // the peers read these stores after the next barrier
 }
 
-template <bool STATS, bool PERSIST, uint32_t RUN, int EPI, bool SYNC = false>
+template <bool STATS, bool PERSIST, uint32_t RUN, int EPI>
 __global__ void __launch_bounds__(256, 5)
 bh_traverse_iw_kernel(const double4 *__restrict__ com, const uint2 *__restrict__ meta, const uint32_t *__restrict__ flags,
                       uint64_t n_bodies, const double *__restrict__ aabb, const double *__restrict__ sx, const double *__restrict__ sy,
@@ -163,30 +163,7 @@ bh_traverse_iw_kernel(const double4 *__restrict__ com, const uint2 *__restrict__
     auto run = [&](auto guard_tag) {
     constexpr bool GUARD = decltype(guard_tag)::value;
     for (;;) {
-        bool skip_tile = false;
-        if constexpr (PERSIST && SYNC) {
-            // CTA-synchronous rounds (experiment, walk_variant 51): the warps of a CTA draw consecutive tiles with ONE
-            // ticket and start them together, so that they sweep the node array side by side and share lines in L1
-            __shared__ unsigned long long s_first;
-            const uint32_t W = blockDim.x >> 5;
-            __syncthreads();
-            if (threadIdx.x == 0) {
-                unsigned long long first = ~0ull;
-                while (probe < n_chunks) {
-                    uint32_t cidx = home + probe;
-                    if (cidx >= n_chunks) cidx -= n_chunks;
-                    const uint32_t t = atomicAdd(&tile_counters[cidx], W);
-                    const uint64_t cand = ((uint64_t) (t / RUN) * n_chunks + cidx) * RUN + (t % RUN);
-                    if (cand < tiles_total) { first = cand; break; }
-                    ++probe;
-                }
-                s_first = first;
-            }
-            __syncthreads();
-            if (s_first == ~0ull) break;
-            tile = s_first + (threadIdx.x >> 5);
-            skip_tile = tile >= tiles_total;
-        } else if constexpr (PERSIST) {
+        if constexpr (PERSIST) {
             bool have = false;
             while (probe < n_chunks) {
                 uint32_t cidx = home + probe;
@@ -207,7 +184,6 @@ bh_traverse_iw_kernel(const double4 *__restrict__ com, const uint2 *__restrict__
         } else {
             if (tile >= tiles_total) break;
         }
-        if (SYNC && skip_tile) continue;
         const uint64_t b = s_begin + tile * 32 + lane;
         const bool valid = b < s_end;
         const uint32_t me = (uint32_t) b;
@@ -330,7 +306,7 @@ int nbk_bh_accel_fused(nb_ctx *ctx, uint64_t s_begin, uint64_t s_end, int epilog
         NB_CUDA(ctx, cudaMemsetAsync(b.stat_totals, 0, 8 * sizeof(unsigned long long), ctx->stream));
         NB_CUDA(ctx, cudaMemsetAsync(b.visits, 0, ctx->n * sizeof(uint32_t), ctx->stream));
         NB_LAUNCH_IW(true, false, 0, NB_EPI_ACCEL, grid);
-    } else if (wv == 50 || wv == 51 || (wv != 20 && count >= (1ull << 19))) {
+    } else if (wv == 50 || (wv != 20 && count >= (1ull << 19))) {
         if (b.walk_ctas_threads != threads) {   // resident CTAs per SM for this CTA size (queried once)
             int per_sm = 0;
             NB_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, bh_traverse_iw_kernel<false, true, 160, NB_EPI_KICK_DRIFT>, threads, 0));
@@ -343,13 +319,7 @@ int nbk_bh_accel_fused(nb_ctx *ctx, uint64_t s_begin, uint64_t s_end, int epilog
         // 84.5 ms; one contiguous chunk per SM 85.2 ms: L1 hit rate up, but 148 distant windows at a time drop the L2
         // hit rate from 92 % to 71 %).  A rank's slice of an 8-GPU run (2^21 bodies) has a tail of ~7 %: a warp needs
         // ~1 ms per tile, so the last round runs on partly empty SMs
-        if (wv == 51 && epilogue == NB_EPI_ACCEL && (160 % (threads / 32)) == 0)   // experiment: CTA-synchronous tile rounds
-            bh_traverse_iw_kernel<false, true, 160, NB_EPI_ACCEL, true><<<pg, threads, 0, ctx->stream>>>(
-                com, b.meta, b.dev_flags, ctx->n, b.aabb_dev, ctx->x, ctx->y, ctx->z, s_begin, s_end, ctx->cfg.theta,
-                ctx->cfg.epsilon2, ctx->cfg.G, out, b.visits, b.stat_totals, b.dev_flags + 8,
-                (uint32_t) std::min<int>(ctx->sm_count, 1024), 1.875);
-        else
-            NB_LAUNCH_EPI(true, 160, pg);
+        NB_LAUNCH_EPI(true, 160, pg);
     } else {
         NB_LAUNCH_EPI(false, 0, grid);
     }

@@ -6,8 +6,9 @@
 // Design (B200-first, not a translation of the SYCL tiles):
 //   * sources are pre-packed into 48-byte AoS records {x,y,z,m,1.5m,1.875m}; a tile of `tile_len` records is ONE
 //     contiguous TMA bulk copy (cp.async.bulk, SASS UBLKCP) into shared memory, completion tracked by mbarriers;
-//   * warp specialisation: 4 consumer warps + 1 producer warp per CTA, NB_NAIVE_STAGES-deep full/empty mbarrier ring,
-//     no __syncthreads in the steady state;
+//   * an NB_NAIVE_STAGES-deep full/empty mbarrier ring, no __syncthreads in the steady state.  Production form
+//     (naive_accel_np_kernel): 4 consumer warps per CTA that take turns issuing the bulk copy two tiles ahead; the
+//     round-1 form with a dedicated producer warp (naive_accel_kernel) is kept as naive_variant 1;
 //   * register blocking: each consumer thread owns IPT target bodies, so one broadcast LDS.128 triple feeds
 //     IPT*32 interactions;
 //   * the FP64 pipe is the roofline.  Per interaction: 3 DADD (r), 3 DFMA (d2 = r.r + eps2), MUFU.RSQ64H seed
@@ -185,6 +186,117 @@ naive_accel_kernel(const nb_src_rec *__restrict__ src, uint32_t n_tiles_total, u
     }
 }
 
+// The same kernel without a dedicated producer warp: 128 threads, all of them consumers.  Consumer warp (t mod 4) issues
+// the bulk copy of tile t + 2 when it starts tile t (the stage it overwrites was last read for tile t - 2, which every
+// warp has left behind once anybody starts tile t + ... see the empty barrier).  The producer warp of the kernel above
+// holds 32 x 158 registers it never uses; without it a CTA needs 20 K registers instead of 25 K and THREE CTAs fit an
+// SM: 12 consumer warps, 3 per scheduler instead of 2 (ncu of the 2-warp form: FP64 pipe 84.5 % active, 0.89 eligible
+// warps per cycle).  Same arithmetic, same summation order, same bits.
+template <int IPT, bool PRECISE, int UNROLL, int MINB>
+__global__ void __launch_bounds__(NB_NAIVE_CONSUMER_WARPS * 32, MINB)
+naive_accel_np_kernel(const nb_src_rec *__restrict__ src, uint32_t n_tiles_total, uint32_t seg_tiles, uint32_t tile_len,
+                      const double *__restrict__ x, const double *__restrict__ y, const double *__restrict__ z,
+                      uint64_t i_begin, uint64_t i_end, double eps2, double G, double *__restrict__ ax,
+                      double *__restrict__ ay, double *__restrict__ az, double *__restrict__ partial) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    uint64_t *full = reinterpret_cast<uint64_t *>(smem_raw);
+    uint64_t *empty = full + NB_NAIVE_STAGES;
+    nb_src_rec *tiles = reinterpret_cast<nb_src_rec *>(smem_raw + 128);
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+    const uint32_t tile_bytes = tile_len * (uint32_t) sizeof(nb_src_rec);
+    const uint32_t t0 = blockIdx.y * seg_tiles;
+    const uint32_t n_tiles = n_tiles_total - t0 < seg_tiles ? n_tiles_total - t0 : seg_tiles;
+    src += (size_t) t0 * tile_len;
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < NB_NAIVE_STAGES; ++s) {
+            mbar_init(&full[s], 1);
+            mbar_init(&empty[s], NB_NAIVE_CONSUMER_WARPS);
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    constexpr uint32_t AHEAD = 2;   // tiles in flight ahead of the one being consumed (NB_NAIVE_STAGES >= AHEAD + 2)
+    if (threadIdx.x == 0) {         // prologue: tiles 0 .. AHEAD-1
+        for (uint32_t t = 0; t < AHEAD && t < n_tiles; ++t) {
+            mbar_expect_tx(&full[t], tile_bytes);
+            bulk_g2s(tiles + (size_t) t * tile_len, src + (size_t) t * tile_len, tile_bytes, &full[t]);
+        }
+    }
+    constexpr int TPB = NB_NAIVE_CONSUMER_WARPS * 32;
+    const uint64_t base = i_begin + (uint64_t) blockIdx.x * (TPB * IPT) + threadIdx.x;
+    double px[IPT], py[IPT], pz[IPT], accx[IPT], accy[IPT], accz[IPT];
+#pragma unroll
+    for (int k = 0; k < IPT; ++k) {
+        uint64_t i = base + (uint64_t) k * TPB;
+        if (i >= i_end) i = i_end - 1;
+        px[k] = x[i]; py[k] = y[i]; pz[k] = z[i];
+        accx[k] = accy[k] = accz[k] = 0.0;
+    }
+    for (uint32_t t = 0; t < n_tiles; ++t) {
+        const uint32_t s = t % NB_NAIVE_STAGES;
+        // this warp's turn to fetch: tile t + AHEAD into the stage tile t + AHEAD - STAGES was read from
+        if ((t % NB_NAIVE_CONSUMER_WARPS) == (uint32_t) warp && lane == 0 && t + AHEAD < n_tiles) {
+            const uint32_t tn = t + AHEAD, sn = tn % NB_NAIVE_STAGES, use = tn / NB_NAIVE_STAGES;
+            if (use > 0) mbar_wait(&empty[sn], (use - 1) & 1);
+            mbar_expect_tx(&full[sn], tile_bytes);
+            bulk_g2s(tiles + (size_t) sn * tile_len, src + (size_t) tn * tile_len, tile_bytes, &full[sn]);
+        }
+        __syncwarp();
+        mbar_wait(&full[s], (t / NB_NAIVE_STAGES) & 1);
+        const double2 *tp = reinterpret_cast<const double2 *>(tiles + (size_t) s * tile_len);
+#pragma unroll(UNROLL)
+        for (uint32_t j = 0; j < tile_len; ++j) {
+            const double2 xy = tp[3 * j + 0];
+            const double2 zm = tp[3 * j + 1];
+            const double2 cc = tp[3 * j + 2];
+#pragma unroll
+            for (int k = 0; k < IPT; ++k) {
+                const double rx = xy.x - px[k];
+                const double ry = xy.y - py[k];
+                const double rz = zm.x - pz[k];
+                double d2 = fma(rx, rx, eps2);
+                d2 = fma(ry, ry, d2);
+                d2 = fma(rz, rz, d2);
+                const double y0 = nb_rsqrt_seed(d2);
+                const double y2 = y0 * y0;
+                const double e = fma(-d2, y2, 1.0);
+                const double y3 = y2 * y0;
+                double q;
+                if (PRECISE) {
+                    const double p = fma(cc.y, e, cc.x);
+                    q = fma(p, e, zm.y);
+                } else {
+                    q = fma(cc.x, e, zm.y);
+                }
+                const double sfac = y3 * q;
+                accx[k] = fma(rx, sfac, accx[k]);
+                accy[k] = fma(ry, sfac, accy[k]);
+                accz[k] = fma(rz, sfac, accz[k]);
+            }
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&empty[s]);
+    }
+    const uint64_t count = i_end - i_begin;
+#pragma unroll
+    for (int k = 0; k < IPT; ++k) {
+        const uint64_t i = base + (uint64_t) k * TPB;
+        if (i < i_end) {
+            if (gridDim.y == 1) {
+                ax[i] = accx[k] * G;
+                ay[i] = accy[k] * G;
+                az[i] = accz[k] * G;
+            } else {
+                double *p = partial + (size_t) blockIdx.y * 3 * count + (i - i_begin);
+                p[0] = accx[k];
+                p[count] = accy[k];
+                p[2 * count] = accz[k];
+            }
+        }
+    }
+}
+
 // deterministic sum of the source segments (ascending), then the final scale by G (NaiveAlgorithm.cpp:349-351)
 __global__ void __launch_bounds__(256)
 naive_reduce_kernel(const double *__restrict__ partial, uint32_t segments, uint64_t i_begin, uint64_t count, double G,
@@ -222,7 +334,7 @@ __global__ void __launch_bounds__(1024) fp64_peak_kernel(double *out, int iters,
     out[(size_t) blockIdx.x * blockDim.x + threadIdx.x] = s;
 }
 
-template <int IPT, bool PRECISE, int UNROLL = 4, int MINB = 2>
+template <int IPT, bool PRECISE, int UNROLL = 4, int MINB = 2, bool NOPROD = false>
 int launch_naive(nb_ctx *ctx, uint32_t n_tiles, uint32_t tile_len, uint64_t i_begin, uint64_t i_end) {
     const uint64_t per_cta = (uint64_t) NB_NAIVE_CONSUMER_WARPS * 32 * IPT;
     const uint64_t count = i_end - i_begin;
@@ -249,9 +361,12 @@ int launch_naive(nb_ctx *ctx, uint32_t n_tiles, uint32_t tile_len, uint64_t i_be
             ctx->naive_partial_cap = need;
         }
     }
-    auto kern = naive_accel_kernel<IPT, PRECISE, UNROLL, MINB>;
+    void (*kern)(const nb_src_rec *, uint32_t, uint32_t, uint32_t, const double *, const double *, const double *, uint64_t,
+                 uint64_t, double, double, double *, double *, double *, double *);
+    if constexpr (NOPROD) kern = naive_accel_np_kernel<IPT, PRECISE, UNROLL, MINB>;
+    else kern = naive_accel_kernel<IPT, PRECISE, UNROLL, MINB>;
     NB_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
-    kern<<<dim3((unsigned) grid, segments), NB_NAIVE_THREADS, smem, ctx->stream>>>(
+    kern<<<dim3((unsigned) grid, segments), NOPROD ? NB_NAIVE_CONSUMER_WARPS * 32 : NB_NAIVE_THREADS, smem, ctx->stream>>>(
         ctx->src, n_tiles, seg_tiles, tile_len, ctx->x, ctx->y, ctx->z, i_begin, i_end, ctx->cfg.epsilon2, ctx->cfg.G, ctx->ax,
         ctx->ay, ctx->az, ctx->naive_partial);
     NB_LAUNCH_CHECK(ctx);
@@ -286,27 +401,23 @@ int nbk_naive_accel(nb_ctx *ctx, uint64_t i_begin, uint64_t i_end) {
     const uint32_t n_tiles = (uint32_t) (n_pad / tile_len);
     const int ipt = ctx->cfg.reserved[0] > 0 ? ctx->cfg.reserved[0] : 4;  // register blocking (tuning knob)
     const bool precise = ctx->cfg.precise_rsqrt != 0;
-    // tuning variants (reserved[2]): {IPT, UNROLL, MINB}; 0 = default
+    // Production form: no dedicated producer warp (naive_accel_np_kernel), IPT 4, unroll 2, two 128-thread CTAs per SM.
+    // Measured at N = 2^19 on B200 (tools/dev_naive_sweep.py, all bit-identical): 258.6 ms, against 262.5 ms for the
+    // producer-warp form of round 1 (naive_variant 1), 260.9 ms with three CTAs per SM (2: a third warp per scheduler
+    // does not help -- the DP pipe, not latency, is what the kernel waits for), 265.5 ms with four (3, 128 registers);
+    // IPT 3 / IPT 2 forms 263 - 267 ms.  naive_variant (cfg.reserved[2]) keeps these three for A/B runs.
     switch (precise ? ctx->cfg.reserved[2] : 0) {
-        case 1: return launch_naive<6, true, 1, 1>(ctx, n_tiles, tile_len, i_begin, i_end);
-        case 2: return launch_naive<6, true, 2, 1>(ctx, n_tiles, tile_len, i_begin, i_end);
-        case 3: return launch_naive<4, true, 3, 2>(ctx, n_tiles, tile_len, i_begin, i_end);
-        case 4: return launch_naive<2, true, 4, 4>(ctx, n_tiles, tile_len, i_begin, i_end);
-        case 5: return launch_naive<2, true, 8, 2>(ctx, n_tiles, tile_len, i_begin, i_end);
-        case 6: return launch_naive<8, true, 1, 1>(ctx, n_tiles, tile_len, i_begin, i_end);
-        case 7: return launch_naive<4, true, 2, 2>(ctx, n_tiles, tile_len, i_begin, i_end);
-        case 8: return launch_naive<4, true, 2, 3>(ctx, n_tiles, tile_len, i_begin, i_end);
-        case 9: return launch_naive<4, true, 4, 1>(ctx, n_tiles, tile_len, i_begin, i_end);
-        case 10: return launch_naive<3, true, 4, 2>(ctx, n_tiles, tile_len, i_begin, i_end);
-        case 11: return launch_naive<3, true, 2, 2>(ctx, n_tiles, tile_len, i_begin, i_end);
+        case 1: return launch_naive<4, true, 2, 2, false>(ctx, n_tiles, tile_len, i_begin, i_end);
+        case 2: return launch_naive<4, true, 2, 3, true>(ctx, n_tiles, tile_len, i_begin, i_end);
+        case 3: return launch_naive<4, true, 2, 4, true>(ctx, n_tiles, tile_len, i_begin, i_end);
         default: break;
     }
-    if (ipt == 1) return precise ? launch_naive<1, true>(ctx, n_tiles, tile_len, i_begin, i_end)
-                                 : launch_naive<1, false>(ctx, n_tiles, tile_len, i_begin, i_end);
-    if (ipt == 4) return precise ? launch_naive<4, true, 2, 2>(ctx, n_tiles, tile_len, i_begin, i_end)   // best of the sweep
-                                 : launch_naive<4, false, 2, 2>(ctx, n_tiles, tile_len, i_begin, i_end);
-    return precise ? launch_naive<2, true>(ctx, n_tiles, tile_len, i_begin, i_end)
-                   : launch_naive<2, false>(ctx, n_tiles, tile_len, i_begin, i_end);
+    if (ipt == 1) return precise ? launch_naive<1, true, 4, 2, true>(ctx, n_tiles, tile_len, i_begin, i_end)
+                                 : launch_naive<1, false, 4, 2, true>(ctx, n_tiles, tile_len, i_begin, i_end);
+    if (ipt == 4) return precise ? launch_naive<4, true, 2, 2, true>(ctx, n_tiles, tile_len, i_begin, i_end)
+                                 : launch_naive<4, false, 2, 2, true>(ctx, n_tiles, tile_len, i_begin, i_end);
+    return precise ? launch_naive<2, true, 4, 2, true>(ctx, n_tiles, tile_len, i_begin, i_end)
+                   : launch_naive<2, false, 4, 2, true>(ctx, n_tiles, tile_len, i_begin, i_end);
 }
 
 int nbk_fp64_peak(nb_ctx *ctx, double *tflops) {

@@ -6,7 +6,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 nb = importlib.import_module("n-body-simulation_b200")
 n = int(sys.argv[1]) if len(sys.argv) > 1 else 1 << 24
-variants = [int(v) for v in (sys.argv[2] if len(sys.argv) > 2 else "5,20,50,0").split(",")]
+variants = [int(v) for v in (sys.argv[2] if len(sys.argv) > 2 else "20,50,0").split(",")]
 wgs = [int(v) for v in (sys.argv[3] if len(sys.argv) > 3 else "128").split(",")]
 gen = sys.argv[4] if len(sys.argv) > 4 else "uniform_sphere"
 m, x, y, z, vx, vy, vz = getattr(nb.generators, gen)(n, seed=1)
