@@ -71,6 +71,7 @@ def parse_args():
     ap.add_argument("--bh-n", type=int, default=1 << 24, help="bodies of the Barnes-Hut workload (default 2^24)")
     ap.add_argument("--no-bh", action="store_true", help="skip the Barnes-Hut measurements")
     ap.add_argument("--no-parity", action="store_true", help="skip the in-run parity gate of the Barnes-Hut line")
+    ap.add_argument("--no-plummer", action="store_true", help="skip the Plummer N=2^24 Barnes-Hut scaling line")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     return ap.parse_args()
 
@@ -320,6 +321,9 @@ def bh_parity_gate(nb, ctx, m, theta, world, samples=256):
     return out
 
 
+_BODIES = {}
+
+
 def time_advance(ctx, torch, dist, dev, world, dt, steps, warmup):
     """steps/s of nb_advance (the time loop's batch of steps): CUDA events on the library's stream, max over ranks."""
     ctx.advance("BarnesHut", dt, max(warmup, 1))
@@ -340,13 +344,19 @@ def time_advance(ctx, torch, dist, dev, world, dt, steps, warmup):
     return ms, ctx.launch_count() - l0
 
 
-def measure_bh(nb, torch, dist, args, rank, local_rank, world, dev, sampler):
+def measure_bh(nb, torch, dist, args, rank, local_rank, world, dev, sampler, gen="uniform_sphere", full=True, static_slices=0):
     """Second half of BASELINE's metric: full Barnes-Hut steps/s (kick-drift, AABB, keys + sort, build, COM, traversal,
-    kick), uniform sphere N = 2^24, theta = 0.5 (configs[3]), targets sharded over the ranks."""
+    kick), uniform sphere N = 2^24, theta = 0.5 (configs[3]), targets sharded over the ranks.  full=False: the light
+    form used for the Plummer scaling line (no e2e, no parity gate)."""
     n = args.bh_n
     theta = 0.5
-    m, x, y, z, vx, vy, vz = nb.generators.uniform_sphere(n, seed=1, velocity_scale=0.3)
-    ctx = nb.Context(device=local_rank, theta=theta, wg_size_barnes_hut=128, world_size=world, rank=rank)
+    if (gen, n) not in _BODIES:
+        _BODIES.clear()   # one body set at a time (3.5 GB of host memory at 2^26)
+        _BODIES[(gen, n)] = (nb.generators.uniform_sphere(n, seed=1, velocity_scale=0.3) if gen == "uniform_sphere"
+                             else getattr(nb.generators, gen)(n, seed=1))
+    m, x, y, z, vx, vy, vz = _BODIES[(gen, n)]
+    ctx = nb.Context(device=local_rank, theta=theta, wg_size_barnes_hut=128, world_size=world, rank=rank,
+                     static_slices=static_slices)
     if world > 1:
         ctx.comm_init(fresh_comm_id(nb, dist, rank, world), world, rank)
     ctx.set_bodies(m, x, y, z, vx, vy, vz)
@@ -355,10 +365,16 @@ def measure_bh(nb, torch, dist, args, rank, local_rank, world, dev, sampler):
 
     # phase times of one step issued call by call (what the reference's time loop does), walk timed without communication
     ctx.enable_timers(True)
-    for _ in range(2):
+    for _ in range(3):
         ctx.leapfrog_part1(dt); ctx.bh_build(); ctx.bh_accel(); ctx.leapfrog_part2(dt)
     timers = ctx.timers()
     ctx.enable_timers(False)
+    walk_per_rank = [timers["Acceleration Kernel Time"]]
+    if world > 1:   # balance of the slices: every rank's walk time of the same step
+        t = torch.zeros(world, dtype=torch.float64, device=dev)
+        t[rank] = timers["Acceleration Kernel Time"]
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        walk_per_rank = [float(v) for v in t.tolist()]
 
     if rank == 0:
         sampler.start()
@@ -372,8 +388,9 @@ def measure_bh(nb, torch, dist, args, rank, local_rank, world, dev, sampler):
     checksum = {"sum_abs_a": float(np.abs(a[0]).sum() + np.abs(a[1]).sum() + np.abs(a[2]).sum()),
                 "sum_abs_x": float(np.abs(p[0]).sum() + np.abs(p[1]).sum() + np.abs(p[2]).sum()),
                 "steps_from_t0": 2 + max(args.warmup, 1) + args.steps}
-    gate = {} if args.no_parity else bh_parity_gate(nb, ctx, m, theta, world)
-    if args.no_parity:
+    no_gate = args.no_parity or not full
+    gate = {} if no_gate else bh_parity_gate(nb, ctx, m, theta, world)
+    if no_gate:
         ctx.bh_enable_stats(True); ctx.bh_build(); ctx.bh_accel()
         tv, ta = ctx.bh_stats(); info = ctx.bh_tree_info(); ctx.bh_enable_stats(False)
         gate = {"visits": tv, "accepts": ta, "max_depth": int(info.max_depth), "num_internal": int(info.num_internal)}
@@ -389,6 +406,8 @@ def measure_bh(nb, torch, dist, args, rank, local_rank, world, dev, sampler):
     # e2e: the reference-facing operator with HOST buffers (H2D of m, x, y, z; build; walk; D2H of the accelerations)
     e2e = None
     try:
+        if not full:
+            raise StopIteration
         pinned = [torch.from_numpy(np.ascontiguousarray(v)).pin_memory() for v in (m, p[0], p[1], p[2])]
         outs = [torch.empty(n, dtype=torch.float64).pin_memory() for _ in range(3)]
         pin_np = [t.numpy() for t in pinned]
@@ -408,14 +427,19 @@ def measure_bh(nb, torch, dist, args, rank, local_rank, world, dev, sampler):
                "call": "nb_op_barnes_hut_accelerations (BarnesHutAlgorithm.hpp:43-46 + BarnesHutOctree.hpp:102-103): pinned host "
                        "m, x, y, z in, tree build, walk, accelerations out; the integrator's 0.5 ms is not part of the operator",
                "sum_abs_a": float(np.abs(out_np[0]).sum() + np.abs(out_np[1]).sum() + np.abs(out_np[2]).sum())}
+    except StopIteration:
+        e2e = None
     except Exception as e:  # noqa: BLE001
         e2e = {"error": repr(e)}
     p2p = ctx.p2p_enabled() if world > 1 else None
     ctx.close()
     return {
         "metric": "Barnes-Hut steps/s", "value": args.steps / (ms * 1e-3), "unit": "steps/s", "ms_per_step": ms / args.steps,
-        "config": {"workload": "Barnes-Hut theta=0.5, uniform sphere N=%d, full step (BASELINE configs[3])" % n,
+        "config": {"workload": ("Barnes-Hut theta=0.5, uniform sphere N=%d, full step (BASELINE configs[3])" % n) if gen == "uniform_sphere"
+                   else "Barnes-Hut theta=0.5, %s sphere N=%d, full step (imbalanced workload for the slice balance, SURVEY 8e)" % (gen, n),
                    "inputs": "larger than L2", "wg_size_barnes_hut": 128,
+                   "slices": "equal count (nb_slice_bounds)" if (static_slices or world == 1 or not p2p) else
+                             "equal cost: cut from the clock ticks each 32-body tile took in the previous walk",
                    "step": "nb_advance: build + walk with the leapfrog half-steps in its epilogue; %s" %
                            ("one GPU" if world == 1 else ("targets sharded x%d, results stored into every rank's arrays by the walk "
                                                           "(IPC peer memory over NVLink) between two barriers" % world if p2p else
@@ -426,6 +450,8 @@ def measure_bh(nb, torch, dist, args, rank, local_rank, world, dev, sampler):
         "internal_nodes_per_body": gate["num_internal"] / n,
         "roofline": roof, "e2e": e2e, "checksum": checksum, "parity": gate.get("parity"),
         "gpu_launches": int(launches), "p2p": p2p, "clocks": clocks,
+        "walk_ms_per_rank": [round(v, 3) for v in walk_per_rank],
+        "walk_max_over_mean": max(walk_per_rank) / (sum(walk_per_rank) / len(walk_per_rank)),
     }
 
 
@@ -642,6 +668,15 @@ def run_ours(args, rank, local_rank, world):
             bh = {"error": repr(e), "traceback": traceback.format_exc()[-1500:]}
             if rank == 0 and bh_sampler.proc:
                 bh_sampler.stop()
+        if not args.no_plummer:   # imbalanced workload: slice balance with equal-cost and (several GPUs) equal-count slices
+            for name, static in (("bh_plummer", 0),) + ((("bh_plummer_static_slices", 1),) if world > 1 else ()):
+                try:
+                    r = measure_bh(nb, torch, dist, args, rank, local_rank, world, dev, ClockSampler(local_rank, interval_ms=50),
+                                   gen="plummer", full=False, static_slices=static)
+                except Exception as e:  # noqa: BLE001
+                    r = {"error": repr(e)}
+                if rank == 0:
+                    extra[name] = r
         if rank == 0 and world == 1:
             for name, fn in (("bh_config3", lambda: measure_config3(nb, torch, args, dev, sm_mhz)),
                              ("config1", lambda: measure_config1(nb))):

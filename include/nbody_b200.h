@@ -72,7 +72,8 @@ typedef struct nb_config {
      *   [3] walk_variant      Barnes-Hut walk: 20 grid-mapped, 50 persistent (SM-local tile queues); 0 picks 50 from 2^19
      *                         bodies per call, else 20
      *   [4] naive_segments    naive: number of source segments per target tile (0: chosen from the grid size)
-     *   [5] (unused)
+     *   [5] static_slices     1: several GPUs keep the equal-count slices of nb_slice_bounds for the Barnes-Hut walk
+     *                         (default: slices of equal cost, from the clock ticks each 32-body tile took in the latest walk)
      *   [6] sort_variant      tree build: 1 full 8-pass (key, slot) sort, 2 packed 5-pass sort; 0: per build (see bh_build.cu)
      *   [7] com_variant       centre of mass: 1 one launch per level instead of one cooperative launch              */
     int32_t reserved[8];

@@ -138,6 +138,8 @@ def default_config(**overrides):
             cfg.reserved[1] = int(v)
         elif k == "naive_segments":
             cfg.reserved[4] = int(v)
+        elif k == "static_slices":
+            cfg.reserved[5] = int(v)
         elif k == "sort_variant":
             cfg.reserved[6] = int(v)
         elif k == "com_variant":

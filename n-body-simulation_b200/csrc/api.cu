@@ -144,7 +144,8 @@ static void release_state(nb_ctx *ctx) {
     ctx->slab_bytes = 0;
     ctx->m = ctx->x = ctx->y = ctx->z = ctx->vx = ctx->vy = ctx->vz = ctx->ax = ctx->ay = ctx->az = ctx->anorm = nullptr;
     for (int k = 0; k < 10; ++k) ctx->alt[k] = nullptr;
-    nb_free(&ctx->id); nb_free(&ctx->id_alt); nb_free(&ctx->e_partial);
+    nb_free(&ctx->id); nb_free(&ctx->id_alt); nb_free(&ctx->e_partial); nb_free(&ctx->tile_start); nb_free(&ctx->dyn_bounds);
+    ctx->tile_cost = nullptr;
     ctx->cap = 0;
 }
 
@@ -155,8 +156,13 @@ static int ensure_capacity(nb_ctx *ctx, uint64_t n) {
     if (need <= ctx->cap) return NB_OK;
     NB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     release_state(ctx);
-    ctx->slab_bytes = (size_t) 21 * need * sizeof(double);
+    const size_t tile_words = ((size_t) need / 32 + 64 + 63) / 64 * 64;
+    ctx->slab_bytes = (size_t) 21 * need * sizeof(double) + tile_words * sizeof(uint32_t);
     NB_CUDA(ctx, cudaMalloc((void **) &ctx->slab, ctx->slab_bytes));
+    ctx->tile_cost = reinterpret_cast<uint32_t *>(ctx->slab + (size_t) 21 * need * sizeof(double));
+    NB_CHECK(nb_alloc(ctx, &ctx->tile_start, tile_words));
+    NB_CHECK(nb_alloc(ctx, &ctx->dyn_bounds, (size_t) NB_MAX_PEERS + 2));
+    ctx->bounds_valid = false;
     double *base = reinterpret_cast<double *>(ctx->slab);
     double **cur[10] = {&ctx->m, &ctx->x, &ctx->y, &ctx->z, &ctx->vx, &ctx->vy, &ctx->vz, &ctx->ax, &ctx->ay, &ctx->az};
     for (int k = 0; k < 10; ++k) { *cur[k] = base + (size_t) k * need; ctx->alt[k] = base + (size_t) (10 + k) * need; }
@@ -268,13 +274,19 @@ static int bh_walk(nb_ctx *ctx, int epilogue, double dt) {
     const bool peers = ctx->world > 1 && ctx->p2p_ok && !ctx->bh.stats_enabled;
     if (ctx->world > 1 && !peers && epilogue != 0)
         return nb_fail(ctx, NB_ERR_INVALID, "fused walk on several GPUs needs mapped peer slabs");
+    // Cost-weighted slices: with peer stores the slice a rank walks need not be the equal-count one of
+    // nb_slice_bounds.  Every walk records what each 32-body tile cost (clock ticks), in every rank's copy; after the
+    // barrier all ranks cut the sorted order into pieces of equal cost -- the same pieces, from the same numbers -- for
+    // the next walk.  The accelerations do not depend on the cut.  cfg.reserved[5] = 1 keeps the equal-count slices.
+    const bool dynamic = peers && ctx->cfg.reserved[5] != 1 && (ctx->cfg.reserved[3] == 50 || e - b >= (1ull << 19));
     if (peers) NB_CHECK(nbk_comm_barrier(ctx));
     {
         nb_timer_scope t(ctx, NB_T_ACCEL);
-        NB_CHECK(nbk_bh_accel_fused(ctx, b, e, epilogue, dt, peers));
+        NB_CHECK(nbk_bh_accel_fused(ctx, b, e, epilogue, dt, peers, dynamic));
     }
     if (peers) NB_CHECK(nbk_comm_barrier(ctx));
     else NB_CHECK(nbk_comm_allgather_accel(ctx, ctx->ax, ctx->ay, ctx->az, ctx->n));
+    if (dynamic) NB_CHECK(nbk_bh_rebalance(ctx));
     return NB_OK;
 }
 

@@ -272,12 +272,7 @@ __device__ __forceinline__ int common_digits(uint64_t hi_a, uint64_t lo_a, uint6
     return NB_MAX_TREE_DEPTH;
 }
 
-// do keys a and b share their first d digits?
-__device__ __forceinline__ bool share_prefix(uint64_t hi_a, uint64_t lo_a, uint64_t hi_b, uint64_t lo_b, int d) {
-    if (d <= 21) return ((hi_a ^ hi_b) >> (63 - 3 * d)) == 0;
-    return hi_a == hi_b && ((lo_a ^ lo_b) >> (63 - 3 * (d - 21))) == 0;
-}
-// the same for sorted body j against the key (hi_i, lo_i): the lower key word of j is only loaded when the question
+// does sorted body j share its first d digits with the key (hi_i, lo_i)?  the lower key word of j is only loaded when the question
 // reaches below level 21 (the searches of emit_kernel are dependent loads; nearly all of them stop at the upper word)
 __device__ __forceinline__ bool shares_prefix_with(const uint64_t *__restrict__ hi, const uint64_t *__restrict__ lo, uint64_t j,
                                                    uint64_t hi_i, uint64_t lo_i, int d) {

@@ -85,6 +85,12 @@ struct nb_walk_out {
     double *x, *y, *z;
     double dt;
     nb_peer_table peers;       // world == 1: local stores only
+    // cost-weighted slices (null when unused): the slots this rank walks are bounds[rank] .. bounds[rank + 1] instead of
+    // the kernel arguments; tile_cost (in the slab: stored to every rank) receives the clock ticks of each tile,
+    // tile_start is local scratch (the start time is parked in memory: no register lives across the cursor loop)
+    const unsigned long long *bounds;
+    uint32_t *tile_cost, *tile_start;
+    int rank;
 };
 
 // store v into slot b of `local` on every rank (the own rank included)
@@ -102,6 +108,14 @@ __device__ __forceinline__ void store_everywhere(const nb_peer_table &pt, double
 template <int EPI>
 __device__ __noinline__ void walk_epilogue(const nb_walk_out &out, uint64_t b, double G, double ax, double ay, double az,
                                            double px, double py, double pz) {
+    if (out.tile_cost && (threadIdx.x & 31) == 0) {   // lane 0 is the first body of the tile: b is a multiple of 32
+        const uint32_t ticks = (uint32_t) clock() - out.tile_start[b >> 5];
+        const nb_peer_table &pt = out.peers;
+        const ptrdiff_t off = reinterpret_cast<unsigned char *>(out.tile_cost) - pt.base[pt.rank];
+#pragma unroll
+        for (int p = 0; p < NB_MAX_PEERS; ++p)
+            if (p < pt.world) reinterpret_cast<uint32_t *>(pt.base[p] + off)[b >> 5] = ticks | 1u;
+    }
     const double gx = __dmul_rn(ax, G), gy = __dmul_rn(ay, G), gz = __dmul_rn(az, G);
     if (EPI != NB_EPI_KICK_DRIFT) {
         store_everywhere(out.peers, out.ax, b, gx);
@@ -147,6 +161,10 @@ bh_traverse_iw_kernel(const double4 *__restrict__ com, const uint2 *__restrict__
     // a failed build (depth / pool flag) leaves no valid tree: produce zeros instead of walking garbage
     const bool tree_ok = flags[0] == 0;
     const int lane = threadIdx.x & 31;
+    if (out.bounds) {   // cost-weighted slice of this rank (multiples of 32) instead of the equal-count one
+        s_begin = out.bounds[out.rank];
+        s_end = out.bounds[out.rank + 1];
+    }
     const uint64_t tiles_total = (s_end - s_begin + 31) >> 5;
     const uint32_t T = PERSIST ? (uint32_t) ((tiles_total + n_chunks - 1) / n_chunks) : 0u;
     uint32_t home = 0, probe = 0;
@@ -186,6 +204,7 @@ bh_traverse_iw_kernel(const double4 *__restrict__ com, const uint2 *__restrict__
         }
         const uint64_t b = s_begin + tile * 32 + lane;
         const bool valid = b < s_end;
+        if (out.tile_cost && lane == 0) out.tile_start[b >> 5] = (uint32_t) clock();
         const uint32_t me = (uint32_t) b;
         double px = 0, py = 0, pz = 0;
         if (valid) { px = sx[b]; py = sy[b]; pz = sz[b]; }
@@ -263,11 +282,62 @@ bh_traverse_iw_kernel(const double4 *__restrict__ com, const uint2 *__restrict__
     }
 }
 
+// New slice bounds from the tile costs of the latest walk: rank r gets the tiles whose cumulative cost lies in
+// [r, r + 1) / world of the total.  One block; thread t owns a contiguous chunk of tiles.  Every rank runs this on the
+// same numbers (the walks stored each tile's cost into every rank's copy) and therefore obtains the same bounds.
+__global__ void __launch_bounds__(1024)
+rebalance_kernel(const uint32_t *__restrict__ tile_cost, uint64_t n_bodies, int world, unsigned long long *__restrict__ bounds) {
+    __shared__ unsigned long long part[1024];
+    const uint64_t n_tiles = (n_bodies + 31) >> 5;
+    const uint64_t chunk = (n_tiles + 1023) / 1024;
+    const uint64_t lo = (uint64_t) threadIdx.x * chunk, hi = lo + chunk < n_tiles ? lo + chunk : n_tiles;
+    unsigned long long sum = 0;
+    for (uint64_t t = lo; t < hi; ++t) sum += tile_cost[t];
+    part[threadIdx.x] = sum;
+    __syncthreads();
+    for (int o = 1; o < 1024; o <<= 1) {   // inclusive scan
+        const unsigned long long v = threadIdx.x >= (unsigned) o ? part[threadIdx.x - o] : 0ull;
+        __syncthreads();
+        part[threadIdx.x] += v;
+        __syncthreads();
+    }
+    const unsigned long long total = part[1023];
+    unsigned long long run = part[threadIdx.x] - sum;   // cost of the tiles before this chunk
+    if (threadIdx.x == 0) { bounds[0] = 0; bounds[world] = n_bodies; }
+    if (total == 0) {   // no costs recorded: equal counts
+        if (threadIdx.x == 0)
+            for (int k = 1; k < world; ++k) bounds[k] = ((n_tiles * (uint64_t) k) / (uint64_t) world) << 5;
+        return;
+    }
+    // cut k lies at cost total * k / world (k = 1 .. world-1, all below total); the intervals [run, next) of the tiles
+    // partition [0, total), so every cut falls into exactly one tile -- the slice boundary goes after that tile
+    auto cut_at = [&](int k) { return (total * (unsigned long long) k) / (unsigned long long) world; };
+    int k = (int) ((run * (unsigned long long) world) / total);
+    if (k < 1) k = 1;
+    while (k < world && cut_at(k) < run) ++k;   // first cut at or after this chunk's start
+    for (uint64_t t = lo; t < hi && k < world; ++t) {
+        const unsigned long long next = run + tile_cost[t];
+        while (k < world && cut_at(k) < next) {
+            const uint64_t slot = (t + 1) << 5;
+            bounds[k] = slot < n_bodies ? slot : n_bodies;
+            ++k;
+        }
+        run = next;
+    }
+}
+
 }  // namespace
+
+int nbk_bh_rebalance(nb_ctx *ctx) {
+    rebalance_kernel<<<1, 1024, 0, ctx->stream>>>(ctx->tile_cost, ctx->n, ctx->world, ctx->dyn_bounds);
+    NB_LAUNCH_CHECK(ctx);
+    ctx->bounds_valid = true;
+    return NB_OK;
+}
 
 // Walk of the bodies in storage slots [s_begin, s_end) (storage order == sorted order after nb_bh_build) with one of the
 // epilogues above; to_peers: store the results into every rank's arrays (requires mapped peer slabs).
-int nbk_bh_accel_fused(nb_ctx *ctx, uint64_t s_begin, uint64_t s_end, int epilogue, double dt, bool to_peers) {
+int nbk_bh_accel_fused(nb_ctx *ctx, uint64_t s_begin, uint64_t s_end, int epilogue, double dt, bool to_peers, bool dynamic_slices) {
     nb_bh_state &b = ctx->bh;
     if (!b.built) return nb_fail(ctx, NB_ERR_INVALID, "nb_bh_accel: call nb_bh_build first");
     if (s_end <= s_begin) return NB_OK;
@@ -286,6 +356,18 @@ int nbk_bh_accel_fused(nb_ctx *ctx, uint64_t s_begin, uint64_t s_end, int epilog
     out.dt = dt;
     out.peers = nbk_peer_table(ctx);
     if (!to_peers) { out.peers.world = 1; out.peers.rank = 0; out.peers.base[0] = ctx->slab; }
+    out.bounds = nullptr;
+    out.tile_cost = out.tile_start = nullptr;
+    out.rank = ctx->rank;
+    if (dynamic_slices && to_peers) {
+        if (!ctx->bounds_valid) {   // first walk of this body set: equal tile counts (tile_cost is all zero)
+            NB_CUDA(ctx, cudaMemsetAsync(ctx->tile_cost, 0, ((ctx->n + 31) / 32) * sizeof(uint32_t), ctx->stream));
+            NB_CHECK(nbk_bh_rebalance(ctx));
+        }
+        out.bounds = ctx->dyn_bounds;
+        out.tile_cost = ctx->tile_cost;
+        out.tile_start = ctx->tile_start;
+    }
     // walk_variant (cfg.reserved[3]): 0 = SM-local tile queues from 2^19 bodies per call (below that the tail of the
     // persistent form costs more than its locality gains), the grid-mapped form otherwise; 20 / 50 force the
     // grid-mapped / persistent form (tests: the two forms are the same arithmetic per body).
@@ -306,7 +388,7 @@ int nbk_bh_accel_fused(nb_ctx *ctx, uint64_t s_begin, uint64_t s_end, int epilog
         NB_CUDA(ctx, cudaMemsetAsync(b.stat_totals, 0, 8 * sizeof(unsigned long long), ctx->stream));
         NB_CUDA(ctx, cudaMemsetAsync(b.visits, 0, ctx->n * sizeof(uint32_t), ctx->stream));
         NB_LAUNCH_IW(true, false, 0, NB_EPI_ACCEL, grid);
-    } else if (wv == 50 || (wv != 20 && count >= (1ull << 19))) {
+    } else if (wv == 50 || dynamic_slices || (wv != 20 && count >= (1ull << 19))) {
         if (b.walk_ctas_threads != threads) {   // resident CTAs per SM for this CTA size (queried once)
             int per_sm = 0;
             NB_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, bh_traverse_iw_kernel<false, true, 160, NB_EPI_KICK_DRIFT>, threads, 0));

@@ -96,6 +96,13 @@ struct nb_ctx {
     // rank's arrays over NVLink, bh_traverse.cu).
     unsigned char *slab = nullptr;
     size_t slab_bytes = 0;
+    // cost-weighted Morton slices (several GPUs): clock ticks every 32-body tile of the sorted order took in the latest
+    // walk (written into every rank's copy by the walk itself; lives in the slab), tile_start = scratch for the tile's
+    // start time, dyn_bounds[r] .. dyn_bounds[r + 1] = the slots rank r walks next (multiples of 32, identical on
+    // every rank because computed from identical costs)
+    uint32_t *tile_cost = nullptr, *tile_start = nullptr;
+    unsigned long long *dyn_bounds = nullptr;
+    bool bounds_valid = false;
     // accelerations: computed for the current positions and stored in the current storage order?  Both turn false when
     // the positions advance / a build leaves them behind (the permutation skips arrays nobody will read).
     bool a_fresh = false, a_order_ok = true;
@@ -211,7 +218,8 @@ int nbk_comm_barrier(nb_ctx *ctx);              // stream-ordered barrier over a
 int nbk_comm_map_peers(nb_ctx *ctx);            // collective: exchange the slab handles, map the peers' slabs
 void nbk_comm_unmap_peers(nb_ctx *ctx);         // collective when peers were mapped (ends with a barrier)
 nb_peer_table nbk_peer_table(const nb_ctx *ctx);
-int nbk_bh_accel_fused(nb_ctx *ctx, uint64_t s_begin, uint64_t s_end, int epilogue, double dt, bool to_peers);
+int nbk_bh_accel_fused(nb_ctx *ctx, uint64_t s_begin, uint64_t s_end, int epilogue, double dt, bool to_peers, bool dynamic_slices = false);
+int nbk_bh_rebalance(nb_ctx *ctx);              // new slice bounds from the tile costs of the latest walk
 int nbk_comm_allreduce_sum(nb_ctx *ctx, double *buf, size_t count);
 
 // ---- device helpers ------------------------------------------------------------------------------------------

@@ -30,11 +30,13 @@ def same(u, v):
 def state(c):
     return c.positions() + c.velocities() + c.accelerations()
 want_p2p = os.environ.get("NB_DISABLE_P2P") is None
-for n, gen in ((20001, "plummer"), (700001, "uniform_sphere")):
+# third case: the persistent walk forced (walk_variant 50) so that the cost-weighted slices are in play on every world
+# size; the accelerations must not depend on where the sorted order is cut
+for n, gen, wv in ((20001, "plummer", 0), (700001, "uniform_sphere", 0), (600011, "plummer", 50)):
     m, x, y, z, vx, vy, vz = getattr(nb.generators, gen)(n, seed=3)
     ref = nb.Context(device=rank, theta=0.5)
     ref.set_bodies(m, x, y, z, vx, vy, vz)
-    ctx = nb.Context(device=rank, theta=0.5, world_size=world, rank=rank)
+    ctx = nb.Context(device=rank, theta=0.5, world_size=world, rank=rank, walk_variant=wv)
     ctx.comm_init(comm_id(), world, rank)
     ctx.set_bodies(m, x, y, z, vx, vy, vz)
     assert ctx.p2p_enabled() == want_p2p, "peer mapping: %%s (expected %%s)" %% (ctx.p2p_enabled(), want_p2p)
