@@ -387,7 +387,7 @@ def measure_bh(nb, torch, dist, args, rank, local_rank, world, dev, sampler, gen
     p = ctx.positions()
     checksum = {"sum_abs_a": float(np.abs(a[0]).sum() + np.abs(a[1]).sum() + np.abs(a[2]).sum()),
                 "sum_abs_x": float(np.abs(p[0]).sum() + np.abs(p[1]).sum() + np.abs(p[2]).sum()),
-                "steps_from_t0": 2 + max(args.warmup, 1) + args.steps}
+                "steps_from_t0": 3 + max(args.warmup, 1) + args.steps}
     no_gate = args.no_parity or not full
     gate = {} if no_gate else bh_parity_gate(nb, ctx, m, theta, world)
     if no_gate:

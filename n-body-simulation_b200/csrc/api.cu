@@ -161,7 +161,7 @@ static int ensure_capacity(nb_ctx *ctx, uint64_t n) {
     NB_CUDA(ctx, cudaMalloc((void **) &ctx->slab, ctx->slab_bytes));
     ctx->tile_cost = reinterpret_cast<uint32_t *>(ctx->slab + (size_t) 21 * need * sizeof(double));
     NB_CHECK(nb_alloc(ctx, &ctx->tile_start, tile_words));
-    NB_CHECK(nb_alloc(ctx, &ctx->dyn_bounds, (size_t) NB_MAX_PEERS + 2));
+    NB_CHECK(nb_alloc(ctx, &ctx->dyn_bounds, (size_t) NB_MAX_PEERS + 2 + need / (32 * 256) + 8));   // bounds + group sums
     ctx->bounds_valid = false;
     double *base = reinterpret_cast<double *>(ctx->slab);
     double **cur[10] = {&ctx->m, &ctx->x, &ctx->y, &ctx->z, &ctx->vx, &ctx->vy, &ctx->vz, &ctx->ax, &ctx->ay, &ctx->az};

@@ -283,53 +283,97 @@ bh_traverse_iw_kernel(const double4 *__restrict__ com, const uint2 *__restrict__
 }
 
 // New slice bounds from the tile costs of the latest walk: rank r gets the tiles whose cumulative cost lies in
-// [r, r + 1) / world of the total.  One block; thread t owns a contiguous chunk of tiles.  Every rank runs this on the
-// same numbers (the walks stored each tile's cost into every rank's copy) and therefore obtains the same bounds.
+// [r, r + 1) / world of the total.  Every rank runs this on the same numbers (the walks stored each tile's cost into
+// every rank's copy) and therefore obtains the same bounds.  Two small kernels: sums over groups of 256 tiles, then one
+// block scans the group sums and one warp per cut finds its group and, inside the group, its tile.
+#define NB_REB_GROUP 256
+__global__ void __launch_bounds__(256)
+rebalance_groups_kernel(const uint32_t *__restrict__ tile_cost, uint64_t n_tiles, unsigned long long *__restrict__ group_sum) {
+    __shared__ unsigned long long ws[8];
+    const uint64_t t = (uint64_t) blockIdx.x * NB_REB_GROUP + threadIdx.x;
+    unsigned long long v = t < n_tiles ? tile_cost[t] : 0ull;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    if ((threadIdx.x & 31) == 0) ws[threadIdx.x >> 5] = v;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        unsigned long long s = 0;
+        for (int w = 0; w < 8; ++w) s += ws[w];
+        group_sum[blockIdx.x] = s;
+    }
+}
+
 __global__ void __launch_bounds__(1024)
-rebalance_kernel(const uint32_t *__restrict__ tile_cost, uint64_t n_bodies, int world, unsigned long long *__restrict__ bounds) {
+rebalance_cuts_kernel(const uint32_t *__restrict__ tile_cost, uint64_t n_bodies, int world, unsigned long long *group_sum,
+                      uint32_t n_groups, unsigned long long *__restrict__ bounds) {
+    __shared__ unsigned long long carry;
     __shared__ unsigned long long part[1024];
     const uint64_t n_tiles = (n_bodies + 31) >> 5;
-    const uint64_t chunk = (n_tiles + 1023) / 1024;
-    const uint64_t lo = (uint64_t) threadIdx.x * chunk, hi = lo + chunk < n_tiles ? lo + chunk : n_tiles;
-    unsigned long long sum = 0;
-    for (uint64_t t = lo; t < hi; ++t) sum += tile_cost[t];
-    part[threadIdx.x] = sum;
+    // inclusive scan of the group sums in place, 1024 groups per round
+    if (threadIdx.x == 0) carry = 0;
     __syncthreads();
-    for (int o = 1; o < 1024; o <<= 1) {   // inclusive scan
-        const unsigned long long v = threadIdx.x >= (unsigned) o ? part[threadIdx.x - o] : 0ull;
+    for (uint32_t base = 0; base < n_groups; base += 1024) {
+        const uint32_t g = base + threadIdx.x;
+        part[threadIdx.x] = g < n_groups ? group_sum[g] : 0ull;
         __syncthreads();
-        part[threadIdx.x] += v;
+        for (int o = 1; o < 1024; o <<= 1) {
+            const unsigned long long v = threadIdx.x >= (unsigned) o ? part[threadIdx.x - o] : 0ull;
+            __syncthreads();
+            part[threadIdx.x] += v;
+            __syncthreads();
+        }
+        if (g < n_groups) group_sum[g] = carry + part[threadIdx.x];
+        __syncthreads();
+        if (threadIdx.x == 1023) carry += part[1023];
         __syncthreads();
     }
-    const unsigned long long total = part[1023];
-    unsigned long long run = part[threadIdx.x] - sum;   // cost of the tiles before this chunk
+    const unsigned long long total = carry;
     if (threadIdx.x == 0) { bounds[0] = 0; bounds[world] = n_bodies; }
-    if (total == 0) {   // no costs recorded: equal counts
-        if (threadIdx.x == 0)
-            for (int k = 1; k < world; ++k) bounds[k] = ((n_tiles * (uint64_t) k) / (uint64_t) world) << 5;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int k = warp + 1;                      // this warp's cut
+    if (k >= world) return;
+    if (total == 0) {                            // no costs recorded yet: equal tile counts
+        if (lane == 0) bounds[k] = ((n_tiles * (uint64_t) k) / (uint64_t) world) << 5;
         return;
     }
-    // cut k lies at cost total * k / world (k = 1 .. world-1, all below total); the intervals [run, next) of the tiles
-    // partition [0, total), so every cut falls into exactly one tile -- the slice boundary goes after that tile
-    auto cut_at = [&](int k) { return (total * (unsigned long long) k) / (unsigned long long) world; };
-    int k = (int) ((run * (unsigned long long) world) / total);
-    if (k < 1) k = 1;
-    while (k < world && cut_at(k) < run) ++k;   // first cut at or after this chunk's start
-    for (uint64_t t = lo; t < hi && k < world; ++t) {
-        const unsigned long long next = run + tile_cost[t];
-        while (k < world && cut_at(k) < next) {
-            const uint64_t slot = (t + 1) << 5;
-            bounds[k] = slot < n_bodies ? slot : n_bodies;
-            ++k;
+    // the cut lies at cost c = total * k / world; it falls into the tile whose cost interval [before, before + cost)
+    // contains c, and the slice boundary goes after that tile
+    const unsigned long long c = (total * (unsigned long long) k) / (unsigned long long) world;
+    uint32_t lo = 0, hi = n_groups - 1;          // first group whose inclusive sum exceeds c
+    while (lo < hi) {
+        const uint32_t mid = (lo + hi) >> 1;
+        if (group_sum[mid] > c) hi = mid; else lo = mid + 1;
+    }
+    unsigned long long before = lo ? group_sum[lo - 1] : 0ull;
+    const uint64_t t0 = (uint64_t) lo * NB_REB_GROUP;
+    uint64_t cut_tile = n_tiles - 1;
+    for (int r = 0; r < NB_REB_GROUP / 32; ++r) {   // 32 tiles at a time: warp-inclusive scan
+        const uint64_t t = t0 + (uint64_t) r * 32 + lane;
+        unsigned long long v = t < n_tiles ? tile_cost[t] : 0ull, inc = v;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const unsigned long long u = __shfl_up_sync(0xffffffffu, inc, o);
+            if (lane >= o) inc += u;
         }
-        run = next;
+        const unsigned hit = __ballot_sync(0xffffffffu, before + inc > c);
+        if (hit) { cut_tile = t0 + (uint64_t) r * 32 + (__ffs(hit) - 1); break; }
+        before += __shfl_sync(0xffffffffu, inc, 31);
+    }
+    if (lane == 0) {
+        const uint64_t slot = (cut_tile + 1) << 5;
+        bounds[k] = slot < n_bodies ? slot : n_bodies;
     }
 }
 
 }  // namespace
 
 int nbk_bh_rebalance(nb_ctx *ctx) {
-    rebalance_kernel<<<1, 1024, 0, ctx->stream>>>(ctx->tile_cost, ctx->n, ctx->world, ctx->dyn_bounds);
+    const uint64_t n_tiles = (ctx->n + 31) / 32;
+    const uint32_t n_groups = (uint32_t) ((n_tiles + NB_REB_GROUP - 1) / NB_REB_GROUP);
+    unsigned long long *group_sum = ctx->dyn_bounds + NB_MAX_PEERS + 2;
+    rebalance_groups_kernel<<<n_groups, 256, 0, ctx->stream>>>(ctx->tile_cost, n_tiles, group_sum);
+    NB_LAUNCH_CHECK(ctx);
+    rebalance_cuts_kernel<<<1, 1024, 0, ctx->stream>>>(ctx->tile_cost, ctx->n, ctx->world, group_sum, n_groups, ctx->dyn_bounds);
     NB_LAUNCH_CHECK(ctx);
     ctx->bounds_valid = true;
     return NB_OK;

@@ -28,15 +28,17 @@ def _uniform(seed, ids, draw):
     return ((k >> np.uint64(11)).astype(np.float64) + 0.5) * (1.0 / 9007199254740992.0)
 
 
-def uniform_sphere(n, seed=1, radius=1.0, total_mass=M_SUN, velocity_scale=0.0):
-    """Uniform-density sphere of radius `radius` AU, equal masses; cold (v=0) unless velocity_scale > 0."""
-    ids = np.arange(n, dtype=np.uint64)
+def uniform_sphere(n, seed=1, radius=1.0, total_mass=M_SUN, velocity_scale=0.0, first_id=0, n_total=None):
+    """Uniform-density sphere of radius `radius` AU, equal masses; cold (v=0) unless velocity_scale > 0.
+    first_id / n_total: bodies first_id .. first_id + n - 1 of a set of n_total (the generator is counter-based, so a
+    large set can be produced in chunks without large temporaries)."""
+    ids = np.arange(first_id, first_id + n, dtype=np.uint64)
     r = radius * np.cbrt(_uniform(seed, ids, 0))
     cos_t = 2.0 * _uniform(seed, ids, 1) - 1.0
     phi = 2.0 * np.pi * _uniform(seed, ids, 2)
     sin_t = np.sqrt(np.maximum(0.0, 1.0 - cos_t * cos_t))
     x, y, z = r * sin_t * np.cos(phi), r * sin_t * np.sin(phi), r * cos_t
-    m = np.full(n, total_mass / n)
+    m = np.full(n, total_mass / (n if n_total is None else n_total))
     if velocity_scale > 0:
         sigma = velocity_scale * np.sqrt(_G_AU_DAY * total_mass / radius)
         vx = sigma * (2.0 * _uniform(seed, ids, 3) - 1.0)
@@ -44,6 +46,8 @@ def uniform_sphere(n, seed=1, radius=1.0, total_mass=M_SUN, velocity_scale=0.0):
         vz = sigma * (2.0 * _uniform(seed, ids, 5) - 1.0)
     else:
         vx = np.zeros(n); vy = np.zeros(n); vz = np.zeros(n)
+    if n_total is not None:
+        return m, x, y, z, vx, vy, vz
     return _dedup(m, x, y, z, vx, vy, vz)
 
 

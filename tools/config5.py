@@ -29,9 +29,19 @@ if world > 1:
     import torch.distributed as dist
     dist.init_process_group("nccl", device_id=dev)
 t0 = time.perf_counter()
-kw = dict(velocity_scale=0.3) if args.gen == "uniform_sphere" else {}
-m, x, y, z, vx, vy, vz = getattr(nb.generators, args.gen)(args.n, seed=1, **kw)
+if args.gen == "uniform_sphere":   # in chunks: 7 arrays of N doubles and nothing else (8 ranks share the host's memory)
+    arrs = [np.empty(args.n) for _ in range(7)]
+    step_ids = 1 << 22
+    for first in range(0, args.n, step_ids):
+        k = min(step_ids, args.n - first)
+        part = nb.generators.uniform_sphere(k, seed=1, velocity_scale=0.3, first_id=first, n_total=args.n)
+        for dst, src in zip(arrs, part):
+            dst[first:first + k] = src
+    m, x, y, z, vx, vy, vz = arrs
+else:
+    m, x, y, z, vx, vy, vz = getattr(nb.generators, args.gen)(args.n, seed=1)
 t_gen = time.perf_counter() - t0
+total_mass = float(m.sum())
 ctx = nb.Context(device=local, theta=args.theta, wg_size_barnes_hut=128, world_size=world, rank=rank)
 if world > 1:
     ids = [nb.comm_unique_id() if rank == 0 else None]
@@ -40,6 +50,9 @@ if world > 1:
 t0 = time.perf_counter()
 ctx.set_bodies(m, x, y, z, vx, vy, vz)
 t_upload = time.perf_counter() - t0
+del m, x, y, z, vx, vy, vz
+if args.gen == "uniform_sphere":
+    del arrs
 ctx.enable_timers(True)
 dt = 1e-3
 
@@ -70,7 +83,12 @@ if args.energy:
     e = [None]
     t_energy = timed(lambda: e.__setitem__(0, ctx.energy()))
     energy = [float(v) for v in e[0]]
-a = ctx.accelerations(); p = ctx.positions(); v = ctx.velocities()
+def abs_sum(get):
+    parts = get()
+    return float(sum(np.abs(c).sum() for c in parts))
+
+
+sum_a, sum_x, sum_v = abs_sum(ctx.accelerations), abs_sum(ctx.positions), abs_sum(ctx.velocities)
 out = {
     "config": "Barnes-Hut theta=%g, %s N=%d, %d GPU(s), energy=%d (BASELINE configs[4])" % (args.theta, args.gen, args.n, world, args.energy),
     "p2p": ctx.p2p_enabled() if world > 1 else None,
@@ -80,12 +98,12 @@ out = {
     "tree": {"internal_nodes": int(info.num_internal), "canonical_nodes": int(info.num_nodes_canonical), "max_depth": int(info.max_depth)},
     "device_memory_in_use_gb": (total_b - free_b) / 2 ** 30,
     "energy": energy,
-    "checksum": {"sum_abs_a": float(sum(np.abs(c).sum() for c in a)), "sum_abs_x": float(sum(np.abs(c).sum() for c in p)),
-                 "sum_abs_v": float(sum(np.abs(c).sum() for c in v))},
+    "checksum": {"sum_abs_a": sum_a, "sum_abs_x": sum_x, "sum_abs_v": sum_v},
+    "host_memory": open("/proc/meminfo").read().split("\n")[0:3],
 }
 if energy is not None and args.gen == "uniform_sphere":
     G = ctx.cfg.G
-    M = float(m.sum())
+    M = total_mass
     analytic = -0.6 * G * M * M / 1.0          # homogeneous sphere of radius 1 AU (the positions moved by one tiny step)
     out["energy_check"] = {"potential_analytic_continuum": analytic, "relative_deviation": (energy[1] - analytic) / abs(analytic),
                            "pairs": args.n * (args.n - 1) / 2.0, "pairs_per_s": args.n * (args.n - 1) / 2.0 / t_energy}

@@ -1,9 +1,9 @@
 #!/bin/bash
 # GPU call 4 (2 GPUs): multi-GPU tests with cost-weighted slices, bench on 2 GPUs with the Plummer balance lines
 mkdir -p gpurun_out
-timeout 1200 python -m pytest tests/test_gpu_multi.py -q -x > gpurun_out/r2_pytest4.log 2>&1; echo "pytest rc=$?" >> gpurun_out/r2_pytest4.log
-tail -15 gpurun_out/r2_pytest4.log
-timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29601 bench.py --gpus 2 --steps 5 --warmup 3 --n 262144 > gpurun_out/r2_bench4_2gpu.json 2> gpurun_out/r2_bench4_2gpu.err; echo "bench2 rc=$?"
+echo skip-tests
+
+timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29601 bench.py --gpus 2 --steps 5 --warmup 3 > gpurun_out/r2_bench4_2gpu.json 2> gpurun_out/r2_bench4_2gpu.err; echo "bench2 rc=$?"
 python - <<'PY'
 import json
 d = json.loads(open("gpurun_out/r2_bench4_2gpu.json").read().strip().splitlines()[-1])
