@@ -198,6 +198,7 @@ int nb_set_bodies(nb_ctx *ctx, uint64_t n, const double *mass, const double *x, 
     ctx->identity_order = true;  // storage order == body-id order until the next Barnes-Hut build
     ctx->a_fresh = false;        // zeros below: in order, but not the forces of these positions
     ctx->a_order_ok = true;
+    ctx->bounds_valid = false;   // cost-weighted slices restart from equal counts for a new body set
     if (ctx->bh.dev_flags) NB_CUDA(ctx, cudaMemsetAsync(ctx->bh.dev_flags, 0, 8 * sizeof(uint32_t), ctx->stream));
     NB_CHECK(h2d(ctx, ctx->m, mass, n));
     NB_CHECK(h2d(ctx, ctx->x, x, n));
@@ -607,6 +608,7 @@ static int upload_for_op(nb_ctx *ctx, uint64_t n, const double *mass, const doub
     if (n == 0 || !mass || !x || !y || !z) return nb_fail(ctx, NB_ERR_INVALID, "operator: need n > 0 and mass/x/y/z");
     NB_CUDA(ctx, cudaSetDevice(ctx->device));
     NB_CHECK(ensure_capacity(ctx, n));
+    if (n != ctx->n) ctx->bounds_valid = false;   // the operator form is called again and again with the same N
     ctx->n = n;
     ctx->bh.built = false;
     ctx->identity_order = true;

@@ -25,6 +25,8 @@
 //      over the sorted keys; each node records its visit rank inside its parent.
 //   5. centre of mass level by level, deepest first (one launch per depth, no atomics): a node sums its children in
 //      octant order (deterministic, bit-identical to the reference's order).
+#include <stdlib.h>
+
 #include <algorithm>
 #include <cooperative_groups.h>
 
@@ -508,6 +510,32 @@ __device__ __forceinline__ void com_level(int depth, const uint32_t *__restrict_
     }
 }
 
+// one node per thread at a time (more threads in flight instead of two chains per thread)
+template <bool COHERENT>
+__device__ __forceinline__ void com_level1(int depth, const uint32_t *__restrict__ level, const uint32_t *__restrict__ list,
+                                           const uint2 *__restrict__ meta, double *com, double *msum4,
+                                           uint32_t tid, uint32_t nthreads) {
+    const uint32_t count = level[depth];
+    const uint32_t *nodes = list + level[NB_LEVELS + depth];
+    for (uint32_t k = tid; k < count; k += nthreads) {
+        const uint32_t p = nodes[k];
+        const uint32_t end = meta[p].x;
+        uint32_t child[8];
+#pragma unroll
+        for (int r = 0; r < 8; ++r) child[r] = NB_NONE;
+        uint32_t ch = p + 1;
+        while (ch < end) {
+            const uint2 mc = meta[ch];
+            const uint32_t rank = nb_meta_rank(mc.y);
+#pragma unroll
+            for (int r = 0; r < 8; ++r)
+                if (rank == (uint32_t) r) child[r] = ch;
+            ch = mc.x > ch ? mc.x : end;
+        }
+        com_sum_and_store<COHERENT>(child, p, com, msum4);
+    }
+}
+
 // one launch per level (fallback when a cooperative launch is not possible)
 __global__ void __launch_bounds__(256)
 com_level_kernel(int depth, const uint32_t *__restrict__ flags_in, const uint32_t *__restrict__ level,
@@ -520,7 +548,9 @@ com_level_kernel(int depth, const uint32_t *__restrict__ flags_in, const uint32_
 // All levels in ONE cooperative launch: the grid is resident as a whole and walks the levels from the deepest internal
 // level up to the root with a grid-wide barrier between two levels (the reference spins on per-node flags inside one
 // work-group, BarnesHutOctree.cpp:327-383).  Replaces 42 dependent launches, most of them for levels below the tree.
-__global__ void __launch_bounds__(256)
+// CHAINS / MINB: two interleaved child chains per thread, or one chain and more resident threads (com_variant).
+template <int CHAINS, int MINB>
+__global__ void __launch_bounds__(256, MINB)
 com_levels_kernel(const uint32_t *__restrict__ flags_in, const uint32_t *__restrict__ level, const uint32_t *__restrict__ list,
                   const uint2 *__restrict__ meta, double *com, double *msum4) {
     if (flags_in[0] & NB_FLAG_POOL) return;   // the same decision in every CTA
@@ -529,7 +559,8 @@ com_levels_kernel(const uint32_t *__restrict__ flags_in, const uint32_t *__restr
     if (depth > NB_MAX_TREE_DEPTH - 1) depth = NB_MAX_TREE_DEPTH - 1;
     const uint32_t tid = blockIdx.x * blockDim.x + threadIdx.x, nthreads = gridDim.x * blockDim.x;
     for (; depth >= 0; --depth) {
-        com_level<true>(depth, level, list, meta, com, msum4, tid, nthreads);
+        if (CHAINS == 2) com_level<true>(depth, level, list, meta, com, msum4, tid, nthreads);
+        else com_level1<true>(depth, level, list, meta, com, msum4, tid, nthreads);
         if (depth > 0) grid.sync();
     }
 }
@@ -661,7 +692,8 @@ int nbk_bh_build(nb_ctx *ctx) {
             int idx_bits = 1;
             while ((1ull << idx_bits) < n) ++idx_bits;
             uint64_t *ws = nullptr;
-            NB_CHECK(nbprim::onesweep_sort_packed(ctx, b.key_hi, b.word_a, b.word_b, n, idx_bits, 5, b.hist, &ws));
+            NB_CHECK(nbprim::onesweep_sort_packed(ctx, b.key_hi, b.word_a, b.word_b, n, idx_bits, 5, b.hist, &ws,
+                                                  getenv("NB_OS_ITEMS") ? atoi(getenv("NB_OS_ITEMS")) : 8));
             unpack_kernel<<<g256, 256, 0, ctx->stream>>>(ws, b.key_hi, n, idx_bits, b.perm, b.key_hi_alt);
             NB_LAUNCH_CHECK(ctx);
             hi_sorted = b.key_hi_alt;
@@ -721,9 +753,14 @@ int nbk_bh_build(nb_ctx *ctx) {
         // fallback when the device or the driver refuses the cooperative launch)
         bool done = false;
         if (ctx->cfg.reserved[7] != 1 && ctx->coop_launch) {
+            // com_variant 0: two chains per thread, 4 CTAs per SM; 2 / 3 / 4: one chain per thread and 5 / 6 / 8 CTAs per SM
+            const void *kern = (const void *) com_levels_kernel<2, 4>;
+            if (ctx->cfg.reserved[7] == 2) kern = (const void *) com_levels_kernel<1, 5>;
+            if (ctx->cfg.reserved[7] == 3) kern = (const void *) com_levels_kernel<1, 6>;
+            if (ctx->cfg.reserved[7] == 4) kern = (const void *) com_levels_kernel<1, 8>;
             if (b.com_ctas_per_sm == 0) {
                 int per_sm = 0;
-                NB_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, com_levels_kernel, 256, 0));
+                NB_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, 256, 0));
                 b.com_ctas_per_sm = per_sm < 1 ? 1 : per_sm;
             }
             // no more CTAs than there are internal nodes to share (< n): small systems get a cheap barrier
@@ -732,7 +769,7 @@ int nbk_bh_build(nb_ctx *ctx) {
             const uint2 *a_meta = b.meta;
             double *a_com = b.com, *a_msum = b.msum;
             void *args[] = {&a_flags, &a_level, &a_list, &a_meta, &a_com, &a_msum};
-            const cudaError_t e = cudaLaunchCooperativeKernel((const void *) com_levels_kernel, dim3(cgrid), dim3(256), args, 0, ctx->stream);
+            const cudaError_t e = cudaLaunchCooperativeKernel(kern, dim3(cgrid), dim3(256), args, 0, ctx->stream);
             if (e == cudaSuccess) {
                 ctx->launches++;
                 done = true;
