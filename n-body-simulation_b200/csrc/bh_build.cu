@@ -367,6 +367,90 @@ emit_kernel(const uint64_t *__restrict__ hi, const uint64_t *__restrict__ lo, co
     leaf_node[i] = (uint32_t) leaf;
 }
 
+// The same emission with the chain nodes of a warp's 32 bodies spread evenly over its lanes.  In emit_kernel a thread
+// loops over the internal nodes first-bodied by its body: 62 % of the bodies have none, a few have three or more, and each
+// node costs a galloping search of its own length -- ncu: 6 of 32 lanes active, issue bound.  Here every lane first writes
+// its body's leaf, then the warp lists its (body, chain index) items in shared memory and each lane takes one item per
+// round: one search per lane, lanes busy as long as there are items.  Same nodes, same values; 0.83 -> 0.73 ms for the
+// "Build subtrees" phase at N = 2^24 (environment NB_EMIT_PER_BODY=1 keeps the per-body loop for A/B).
+__global__ void __launch_bounds__(128)
+emit_balanced_kernel(const uint64_t *__restrict__ hi, const uint64_t *__restrict__ lo, const int32_t *__restrict__ delta,
+                     const uint32_t *__restrict__ base, uint64_t n, uint64_t cap_nodes, uint32_t *__restrict__ flags,
+                     uint2 *__restrict__ meta, uint32_t *__restrict__ body_count, uint32_t *__restrict__ leaf_node) {
+    constexpr int SLOTS = 128;                       // items listed per pass and warp
+    __shared__ uint16_t s_owner[4][SLOTS];           // item -> source lane | chain index << 5
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const uint64_t i = (uint64_t) blockIdx.x * blockDim.x + threadIdx.x;
+    const uint64_t total_internal = flags[1];
+    const uint64_t M = n + total_internal;
+    if (M > cap_nodes) {  // reference: silent overflow of the 16N pool (README.md:117-118); here: reported
+        if (i == 0) atomicOr(&flags[0], NB_FLAG_POOL);
+        return;
+    }
+    const bool valid = i < n;
+    uint64_t hi_i = 0;
+    int d_prev = -1, d_cur = -1;
+    uint32_t c = 0;
+    uint64_t head = 0;
+    if (valid) {
+        hi_i = hi[i];
+        d_prev = i > 0 ? delta[i - 1] : -1;
+        d_cur = delta[i];
+        c = d_cur > d_prev ? (uint32_t) (d_cur - d_prev) : 0u;
+        head = i + base[i];
+        const uint64_t leaf = head + c;
+        const int leaf_parent_depth = d_cur > d_prev ? d_cur : d_prev;  // -1 only when N == 1
+        const uint64_t lo_i = leaf_parent_depth >= 21 ? lo[i] : 0ull;   // the lower key word only below level 21
+        const uint32_t leaf_dig = leaf_parent_depth >= 0 ? digit_at(hi_i, lo_i, leaf_parent_depth) : 0u;
+        meta[leaf] = make_uint2((uint32_t) (leaf + 1), NB_LEAF_FLAG | (leaf_dig << NB_DIGIT_SHIFT) | (uint32_t) i);
+        body_count[leaf] = 1;
+        leaf_node[i] = (uint32_t) leaf;
+    }
+    // items of the warp: exclusive prefix of the chain lengths
+    uint32_t inc = c;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const uint32_t t = __shfl_up_sync(0xffffffffu, inc, o);
+        if (lane >= o) inc += t;
+    }
+    const uint32_t off = inc - c, W = __shfl_sync(0xffffffffu, inc, 31);
+    const uint32_t ilo = (uint32_t) i, ihi = (uint32_t) (i >> 32);
+    for (uint32_t pass = 0; pass < W; pass += SLOTS) {
+        __syncwarp();
+        for (uint32_t k = 0; k < c; ++k) {
+            const uint32_t t = off + k;
+            if (t >= pass && t < pass + SLOTS) s_owner[w][t - pass] = (uint16_t) (lane | (k << 5));
+        }
+        __syncwarp();
+        const uint32_t count = W - pass < (uint32_t) SLOTS ? W - pass : (uint32_t) SLOTS;
+        for (uint32_t t0 = 0; t0 < count; t0 += 32) {     // warp-uniform trip count: the shuffles need every lane
+            const uint32_t t = t0 + lane;
+            const bool have = t < count;
+            const uint32_t o = have ? s_owner[w][t] : 0u;
+            const int src = (int) (o & 31u), k = (int) (o >> 5);
+            const uint64_t body = ((uint64_t) __shfl_sync(0xffffffffu, ihi, src) << 32) | __shfl_sync(0xffffffffu, ilo, src);
+            const uint64_t key = ((uint64_t) __shfl_sync(0xffffffffu, (uint32_t) (hi_i >> 32), src) << 32) |
+                                 __shfl_sync(0xffffffffu, (uint32_t) hi_i, src);
+            const int dp = __shfl_sync(0xffffffffu, d_prev, src);
+            const uint32_t head_lo = __shfl_sync(0xffffffffu, (uint32_t) head, src), head_hi = __shfl_sync(0xffffffffu, (uint32_t) (head >> 32), src);
+            if (!have) continue;
+            const int d = dp + 1 + k;
+            const uint64_t key_lo = d > 21 ? lo[body] : 0ull;
+            uint64_t r = body + 1, step = 1;   // body + 1 shares d_cur >= d digits
+            while (r + step < n && shares_prefix_with(hi, lo, r + step, key, key_lo, d)) { r += step; step <<= 1; }
+            while (step > 1) {
+                step >>= 1;
+                if (r + step < n && shares_prefix_with(hi, lo, r + step, key, key_lo, d)) r += step;
+            }
+            const uint64_t node = (((uint64_t) head_hi << 32) | head_lo) + (uint64_t) k;
+            const uint64_t skip = r + 1 < n ? (r + 1) + base[r + 1] : M;
+            const uint32_t dig = d > 0 ? digit_at(key, key_lo, d - 1) : 0u;  // visit rank of this cell inside its parent
+            meta[node] = make_uint2((uint32_t) skip, ((uint32_t) d << NB_DEPTH_SHIFT) | dig);
+            body_count[node] = (uint32_t) (r - body + 1);
+        }
+    }
+}
+
 // ---- 4b. per-depth lists of internal nodes (dense work lists for the centre-of-mass levels) ---------------------------------
 // level[0..63] = node count per depth (delta_kernel), level[64..127] = start of the depth's segment in `list`,
 // level[128..191] = fill cursor
@@ -510,32 +594,6 @@ __device__ __forceinline__ void com_level(int depth, const uint32_t *__restrict_
     }
 }
 
-// one node per thread at a time (more threads in flight instead of two chains per thread)
-template <bool COHERENT>
-__device__ __forceinline__ void com_level1(int depth, const uint32_t *__restrict__ level, const uint32_t *__restrict__ list,
-                                           const uint2 *__restrict__ meta, double *com, double *msum4,
-                                           uint32_t tid, uint32_t nthreads) {
-    const uint32_t count = level[depth];
-    const uint32_t *nodes = list + level[NB_LEVELS + depth];
-    for (uint32_t k = tid; k < count; k += nthreads) {
-        const uint32_t p = nodes[k];
-        const uint32_t end = meta[p].x;
-        uint32_t child[8];
-#pragma unroll
-        for (int r = 0; r < 8; ++r) child[r] = NB_NONE;
-        uint32_t ch = p + 1;
-        while (ch < end) {
-            const uint2 mc = meta[ch];
-            const uint32_t rank = nb_meta_rank(mc.y);
-#pragma unroll
-            for (int r = 0; r < 8; ++r)
-                if (rank == (uint32_t) r) child[r] = ch;
-            ch = mc.x > ch ? mc.x : end;
-        }
-        com_sum_and_store<COHERENT>(child, p, com, msum4);
-    }
-}
-
 // one launch per level (fallback when a cooperative launch is not possible)
 __global__ void __launch_bounds__(256)
 com_level_kernel(int depth, const uint32_t *__restrict__ flags_in, const uint32_t *__restrict__ level,
@@ -548,9 +606,11 @@ com_level_kernel(int depth, const uint32_t *__restrict__ flags_in, const uint32_
 // All levels in ONE cooperative launch: the grid is resident as a whole and walks the levels from the deepest internal
 // level up to the root with a grid-wide barrier between two levels (the reference spins on per-node flags inside one
 // work-group, BarnesHutOctree.cpp:327-383).  Replaces 42 dependent launches, most of them for levels below the tree.
-// CHAINS / MINB: two interleaved child chains per thread, or one chain and more resident threads (com_variant).
-template <int CHAINS, int MINB>
-__global__ void __launch_bounds__(256, MINB)
+// Measured at N = 2^24 (gpurun_out/r2_build_ab.log): one chain per thread with 5 / 6 CTAs per SM 1.27 / 1.30 ms, with 8
+// CTAs per SM (32 registers) 1.43 ms, two chains per thread 1.27 ms -- the pass does not respond to more loads in flight:
+// it moves 3.2 GB of scattered 32-byte sectors (2.68 GB read: 8-byte node words and 32-byte sums of the children) at 41 %
+// DRAM-active, which is what random sector traffic gets.
+__global__ void __launch_bounds__(256, 4)
 com_levels_kernel(const uint32_t *__restrict__ flags_in, const uint32_t *__restrict__ level, const uint32_t *__restrict__ list,
                   const uint2 *__restrict__ meta, double *com, double *msum4) {
     if (flags_in[0] & NB_FLAG_POOL) return;   // the same decision in every CTA
@@ -559,8 +619,7 @@ com_levels_kernel(const uint32_t *__restrict__ flags_in, const uint32_t *__restr
     if (depth > NB_MAX_TREE_DEPTH - 1) depth = NB_MAX_TREE_DEPTH - 1;
     const uint32_t tid = blockIdx.x * blockDim.x + threadIdx.x, nthreads = gridDim.x * blockDim.x;
     for (; depth >= 0; --depth) {
-        if (CHAINS == 2) com_level<true>(depth, level, list, meta, com, msum4, tid, nthreads);
-        else com_level1<true>(depth, level, list, meta, com, msum4, tid, nthreads);
+        com_level<true>(depth, level, list, meta, com, msum4, tid, nthreads);
         if (depth > 0) grid.sync();
     }
 }
@@ -692,8 +751,7 @@ int nbk_bh_build(nb_ctx *ctx) {
             int idx_bits = 1;
             while ((1ull << idx_bits) < n) ++idx_bits;
             uint64_t *ws = nullptr;
-            NB_CHECK(nbprim::onesweep_sort_packed(ctx, b.key_hi, b.word_a, b.word_b, n, idx_bits, 5, b.hist, &ws,
-                                                  getenv("NB_OS_ITEMS") ? atoi(getenv("NB_OS_ITEMS")) : 8));
+            NB_CHECK(nbprim::onesweep_sort_packed(ctx, b.key_hi, b.word_a, b.word_b, n, idx_bits, 5, b.hist, &ws));
             unpack_kernel<<<g256, 256, 0, ctx->stream>>>(ws, b.key_hi, n, idx_bits, b.perm, b.key_hi_alt);
             NB_LAUNCH_CHECK(ctx);
             hi_sorted = b.key_hi_alt;
@@ -735,7 +793,11 @@ int nbk_bh_build(nb_ctx *ctx) {
         NB_LAUNCH_CHECK(ctx);
         uint32_t *tile_tmp = b.hist;  // scan scratch (sort is finished)
         NB_CHECK(nbprim::exclusive_scan_u32(ctx, b.chain_cnt, b.chain_base, n, tile_tmp, b.dev_flags + 1));
-        emit_kernel<<<g128, 128, 0, ctx->stream>>>(hi, lo, b.delta, b.chain_base, n, b.cap_nodes, b.dev_flags, b.meta,
+        if (getenv("NB_EMIT_PER_BODY"))
+            emit_kernel<<<g128, 128, 0, ctx->stream>>>(hi, lo, b.delta, b.chain_base, n, b.cap_nodes, b.dev_flags, b.meta,
+                                                       b.body_count, b.leaf_node);
+        else
+            emit_balanced_kernel<<<g128, 128, 0, ctx->stream>>>(hi, lo, b.delta, b.chain_base, n, b.cap_nodes, b.dev_flags, b.meta,
                                                    b.body_count, b.leaf_node);
         NB_LAUNCH_CHECK(ctx);
         // dense per-depth node lists for the centre-of-mass levels
@@ -753,11 +815,7 @@ int nbk_bh_build(nb_ctx *ctx) {
         // fallback when the device or the driver refuses the cooperative launch)
         bool done = false;
         if (ctx->cfg.reserved[7] != 1 && ctx->coop_launch) {
-            // com_variant 0: two chains per thread, 4 CTAs per SM; 2 / 3 / 4: one chain per thread and 5 / 6 / 8 CTAs per SM
-            const void *kern = (const void *) com_levels_kernel<2, 4>;
-            if (ctx->cfg.reserved[7] == 2) kern = (const void *) com_levels_kernel<1, 5>;
-            if (ctx->cfg.reserved[7] == 3) kern = (const void *) com_levels_kernel<1, 6>;
-            if (ctx->cfg.reserved[7] == 4) kern = (const void *) com_levels_kernel<1, 8>;
+            const void *kern = (const void *) com_levels_kernel;
             if (b.com_ctas_per_sm == 0) {
                 int per_sm = 0;
                 NB_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, 256, 0));

@@ -16,7 +16,7 @@ for cv in variants:
     c.enable_timers(True)
     acc = {}
     for s in range(6):
-        c.leapfrog_part1(1e-3); c.bh_build(); c.synchronize()
+        c.leapfrog_part1(1e-3); c.bh_build(); c.bh_accel_range(0, 64); c.synchronize()
         t = c.timers()
         if s >= 2:
             for k, v in t.items():
@@ -26,6 +26,6 @@ for cv in variants:
     info = c.bh_tree_info()
     c2 = c.bh_export_canonical() if n <= (1 << 20) else None
     chk = (int(info.num_internal), int(info.max_depth))
-    print("N=%d NB_OS_ITEMS=%s com_variant=%d: %s tree %s" % (n, os.environ.get("NB_OS_ITEMS", "8"), cv,
+    print("N=%d NB_OS_ITEMS=%s emit=%s com_variant=%d: %s tree %s" % (n, os.environ.get("NB_OS_ITEMS", "8"), "per-body" if os.environ.get("NB_EMIT_PER_BODY") else "balanced", cv,
           {k: round(float(np.median(v)), 3) for k, v in acc.items() if np.median(v) > 0 and k not in ("Leapfrog Part 1", "Acceleration Kernel Time")}, chk), flush=True)
     c.close()
