@@ -36,8 +36,10 @@ def _run(cmd, verbose):
     subprocess.check_call(cmd)
 
 
-def build_library(force=False, verbose=False, ptxas_info=False):
-    objdir = os.path.join(HERE, "build")
+def build_library(force=False, verbose=False, ptxas_info=False, out_dir=None):
+    """out_dir: build objects and the library there instead of in-tree (a clean rebuild that leaves the tree alone)."""
+    objdir = os.path.join(out_dir or HERE, "build")
+    lib = os.path.join(out_dir, "libnbody_b200.so") if out_dir else LIB
     os.makedirs(objdir, exist_ok=True)
     headers = [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".cuh", ".h"))]
     headers.append(os.path.join(ROOT, "include", "nbody_b200.h"))
@@ -55,9 +57,10 @@ def build_library(force=False, verbose=False, ptxas_info=False):
     failed = [src for src, p in procs if p.wait() != 0]
     if failed:
         raise RuntimeError("nvcc failed for: " + ", ".join(failed))
-    if force or procs or _newer(LIB, objs):
-        _run([NVCC, "-shared", "-o", LIB] + objs + ["-lcudart", "-ldl", "-Xlinker", "-z,defs", "-Wno-deprecated-gpu-targets"], verbose)
-    return LIB
+    if force or procs or _newer(lib, objs):
+        _run([NVCC, "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", lib] + objs +
+             ["-lcudart", "-ldl", "-Xlinker", "-z,defs"], verbose)
+    return lib
 
 
 def build_host(force=False, verbose=False):

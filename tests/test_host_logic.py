@@ -163,6 +163,24 @@ def test_library_exports_every_declared_symbol(nb):
     assert L.nb_abi_version() == 1
 
 
+def test_clean_rebuild_from_sources(nb, tmp_path):
+    """The in-tree library is reused when it is newer than its sources (build(): mtime check).  This is the clean build:
+    every .cu compiled for sm_100a from scratch into a scratch directory (nvcc cross-compiles without a GPU), linked with
+    no undefined symbols, exporting every entry point the header declares, carrying sm_100a code only."""
+    import ctypes
+    import subprocess
+    build = __import__("importlib").import_module("n-body-simulation_b200.build")
+    lib = build.build_library(force=True, out_dir=str(tmp_path))
+    assert os.path.dirname(lib) == str(tmp_path) and os.path.getsize(lib) > 100000
+    L = ctypes.CDLL(lib)
+    binding = __import__("importlib").import_module("n-body-simulation_b200.binding")
+    for sym in binding.EXPORTED_SYMBOLS:
+        assert hasattr(L, sym), sym
+    assert L.nb_abi_version() == 1
+    elf = subprocess.run(["cuobjdump", "-lelf", lib], capture_output=True, text=True).stdout
+    assert "sm_100a" in elf and not re.search(r"sm_(?!100a)\d+", elf), elf[:400]
+
+
 def test_default_config_matches_reference_defaults(nb, oracle):
     cfg = nb.default_config()
     assert cfg.G == oracle.gravitational_constant() and cfg.epsilon2 == oracle.epsilon2()
