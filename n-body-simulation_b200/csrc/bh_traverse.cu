@@ -384,6 +384,7 @@ int nbk_bh_rebalance(nb_ctx *ctx) {
 int nbk_bh_accel_fused(nb_ctx *ctx, uint64_t s_begin, uint64_t s_end, int epilogue, double dt, bool to_peers, bool dynamic_slices) {
     nb_bh_state &b = ctx->bh;
     if (!b.built) return nb_fail(ctx, NB_ERR_INVALID, "nb_bh_accel: call nb_bh_build first");
+    if (dynamic_slices && to_peers) { s_begin = 0; s_end = ctx->n; }   // the kernel reads its slice from dyn_bounds: size the grid for any
     if (s_end <= s_begin) return NB_OK;
     if (to_peers && !ctx->p2p_ok) return nb_fail(ctx, NB_ERR_INVALID, "walk with peer stores: peer slabs are not mapped");
     int threads = ctx->cfg.wg_size_barnes_hut;  // --wg_size_barnes_hut -> CTA size (multiple of 32, <= 256)
