@@ -280,6 +280,12 @@ static int bh_walk(nb_ctx *ctx, int epilogue, double dt) {
     // barrier all ranks cut the sorted order into pieces of equal cost -- the same pieces, from the same numbers -- for
     // the next walk.  The accelerations do not depend on the cut.  cfg.reserved[5] = 1 keeps the equal-count slices.
     const bool dynamic = peers && ctx->cfg.reserved[5] != 1 && (ctx->cfg.reserved[3] == 50 || e - b >= (1ull << 19));
+    if (dynamic && !ctx->bounds_valid) {
+        // first walk of this body set: no costs yet -> equal tile counts.  BEFORE the barrier: once a rank has passed it, its
+        // walk stores tile costs into this rank's copy, which a later memset would wipe (and the ranks' cuts would differ)
+        NB_CUDA(ctx, cudaMemsetAsync(ctx->tile_cost, 0, ((ctx->n + 31) / 32) * sizeof(uint32_t), ctx->stream));
+        NB_CHECK(nbk_bh_rebalance(ctx));
+    }
     if (peers) NB_CHECK(nbk_comm_barrier(ctx));
     {
         nb_timer_scope t(ctx, NB_T_ACCEL);

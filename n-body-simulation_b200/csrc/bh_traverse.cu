@@ -405,10 +405,7 @@ int nbk_bh_accel_fused(nb_ctx *ctx, uint64_t s_begin, uint64_t s_end, int epilog
     out.tile_cost = out.tile_start = nullptr;
     out.rank = ctx->rank;
     if (dynamic_slices && to_peers) {
-        if (!ctx->bounds_valid) {   // first walk of this body set: equal tile counts (tile_cost is all zero)
-            NB_CUDA(ctx, cudaMemsetAsync(ctx->tile_cost, 0, ((ctx->n + 31) / 32) * sizeof(uint32_t), ctx->stream));
-            NB_CHECK(nbk_bh_rebalance(ctx));
-        }
+        if (!ctx->bounds_valid) return nb_fail(ctx, NB_ERR_INVALID, "walk with cost-weighted slices: no slice bounds yet");
         out.bounds = ctx->dyn_bounds;
         out.tile_cost = ctx->tile_cost;
         out.tile_start = ctx->tile_start;
