@@ -224,29 +224,7 @@ bh_traverse_iw_kernel(const double4 *__restrict__ com, const uint2 *__restrict__
                 // exactly 0.0 either way (the build stores a finite record for them), so only the instrumented build
                 // pays for the check that keeps the visit counts identical to the reference's.
                 const bool massless = STATS && (__double2hiint(c.w) | __double2loint(c.w)) == 0;
-                bool interact;
-                if (mt.y & NB_LEAF_FLAG) {
-                    interact = (mt.y & NB_PAYLOAD_MASK) != me && !massless;  // own leaf skipped (:349)
-                    next = cur + 1;
-                    if (STATS) nvis += interact ? 1u : 0u;
-                } else if (massless) {
-                    interact = false;
-                    next = max(mt.x, cur + 1);
-                } else {
-                    // mt.y = depth << 21 | visit rank (3 bits), so V = hiword(D) + (depth << 21) + rank is ONE add.  The
-                    // rank only widens the undecided band: accept for sure when V - 7 >= W_0 + 2 (V > W_0 + 8), open
-                    // for sure when V <= W_0 - 2
-                    const int V = __double2hiint(D) + (int) mt.y;
-                    bool accept = V > Whi;
-                    if ((GUARD && mt.y >= t_lim) || (!accept && V >= Wlo)) {
-                        // undecided, or a depth where eps2 matters: the oracle's exact expression, no contraction
-                        accept = exact_accept(dx, dy, dz, edge0, mt.y >> NB_DEPTH_SHIFT, theta);
-                    }
-                    interact = accept;
-                    next = accept ? mt.x : cur + 1;  // a skip link points behind the node's subtree: always > cur
-                    if (STATS) nvis += 1u;
-                }
-                if (interact) {
+                auto force = [&]() {
                     if (STATS) nacc += 1u;
                     const double y0 = nb_rsqrt_seed(D);
                     const double y2 = y0 * y0;
@@ -258,6 +236,32 @@ bh_traverse_iw_kernel(const double4 *__restrict__ com, const uint2 *__restrict__
                     ax = fma(dx, s, ax);
                     ay = fma(dy, s, ay);
                     az = fma(dz, s, az);
+                };
+                if (mt.y & NB_LEAF_FLAG) {
+                    const bool interact = (mt.y & NB_PAYLOAD_MASK) != me && !massless;  // own leaf skipped (:349)
+                    next = cur + 1;
+                    if (STATS) nvis += interact ? 1u : 0u;
+                    if (interact) force();
+                } else if (massless) {
+                    next = max(mt.x, cur + 1);
+                } else {
+                    // mt.y = depth << 21 | visit rank (3 bits), so V = hiword(D) + (depth << 21) + rank is ONE add.  The
+                    // rank only widens the undecided band: accept for sure when V - 7 >= W_0 + 2 (V > W_0 + 8), open
+                    // for sure when V <= W_0 - 2
+                    const int V = __double2hiint(D) + (int) mt.y;
+                    if (STATS) nvis += 1u;
+                    const bool guarded = GUARD && mt.y >= t_lim;
+                    if (V > Whi && !guarded) {
+                        next = mt.x;      // a skip link points behind the node's subtree: always > cur
+                        force();
+                    } else if (V < Wlo && !guarded) {
+                        next = cur + 1;
+                    } else {
+                        // undecided, or a depth where eps2 matters: the oracle's exact expression, no contraction
+                        const bool accept = exact_accept(dx, dy, dz, edge0, mt.y >> NB_DEPTH_SHIFT, theta);
+                        next = accept ? mt.x : cur + 1;
+                        if (accept) force();
+                    }
                 }
             }
             cur = __reduce_min_sync(0xffffffffu, next);
