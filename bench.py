@@ -543,8 +543,10 @@ def measure_config1(nb):
             continue
         with tempfile.TemporaryDirectory() as d:
             t0 = time.perf_counter()
+            env = dict(os.environ)
+            env.setdefault("CUDA_VISIBLE_DEVICES", "0")   # CUDA start-up time grows with the number of visible devices
             r = subprocess.run([exe, "--file=" + fixture, "--dt=1h", "--t_end=365d", "--vs=1d", "--vs_dir=" + d,
-                                "--algorithm=naive", "--opt_stage=2"], capture_output=True, text=True, timeout=600)
+                                "--algorithm=naive", "--opt_stage=2"], capture_output=True, text=True, timeout=600, env=env)
             out[name + "_wall_s"] = time.perf_counter() - t0
             out[name + "_rc"] = r.returncode
             for root, _, files in os.walk(d):
