@@ -55,9 +55,10 @@ BH_DP_PER_OPEN = 6.0                 # an opened node stops after the distance (
 FP64_LANES_PER_SM = 64.0             # DP pipe: 64 lanes per SM and clock (one DFMA per lane)
 NAIVE_TILE = 256                     # --block_size used for the benchmark (shared-memory tile length)
 # dram__bytes_read.sum + dram__bytes_write.sum per launch, NOT measured in this run: from the `ncu --set full` captures
-# summarised under profiles/ (naive: N = 2^20, profiles/naive_accel_r01b.txt; walk: N = 2^24, profiles/bh_traverse_r01c.txt)
-NCU_TRAFFIC_BYTES = {("naive", 1 << 20): 123.167744e6 + 55.533824e6, ("bh", 1 << 24): 2.557424e9 + 400.486656e6}
-NCU_TRAFFIC_SOURCE = {"naive": "profiles/naive_accel_r01b.txt", "bh": "profiles/bh_traverse_r01c.txt"}
+# summarised under profiles/ (naive: N = 2^20, profiles/naive_accel_r02.txt -- 444 MB of the writes are the per-segment
+# partial sums; walk: N = 2^24, acceleration-only form, profiles/bh_step_r02.txt)
+NCU_TRAFFIC_BYTES = {("naive", 1 << 20): 168.282112e6 + 443.659520e6, ("bh", 1 << 24): 2.533143e9 + 399.558912e6}
+NCU_TRAFFIC_SOURCE = {"naive": "profiles/naive_accel_r02.txt", "bh": "profiles/bh_step_r02.txt"}
 PARITY_TOL = 1e-10
 
 
