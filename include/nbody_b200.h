@@ -74,7 +74,8 @@ typedef struct nb_config {
      *   [4] naive_segments    naive: number of source segments per target tile (0: chosen from the grid size)
      *   [5] static_slices     1: several GPUs keep the equal-count slices of nb_slice_bounds for the Barnes-Hut walk
      *                         (default: slices of equal cost, from the clock ticks each 32-body tile took in the latest walk)
-     *   [6] sort_variant      tree build: 1 full 8-pass (key, slot) sort, 2 packed 5-pass sort; 0: per build (see bh_build.cu)
+     *   [6] sort_variant      tree build: 1 full 8-pass (key, slot) sort, 2 / 3 packed 5-pass / 4-pass sort; 0: per build (see
+     *                         bh_build.cu)
      *   [7] com_variant       centre of mass: 1 one launch per level instead of one cooperative launch
      * Environment (developer A/B only): NB_DISABLE_P2P=1 keeps the NCCL all-gather path; NB_EMIT_PER_BODY=1 the round-1
      * node emission kernel.                                                                                          */

@@ -18,6 +18,9 @@ HOST_CXX = "/usr/bin/g++" if os.path.exists("/usr/bin/g++") else "g++"
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17", "-Xcompiler", "-fPIC",
               "-ccbin", HOST_CXX, "--expt-relaxed-constexpr"]
 
+# developer A/B builds: extra nvcc flags (e.g. -DNB_NODE_WORDS=8) for a library built into another directory
+NVCC_FLAGS += os.environ.get("NB_NVCC_EXTRA", "").split()
+
 CU_SOURCES = ["api.cu", "naive.cu", "integrator.cu", "energy.cu", "bh_build.cu", "bh_traverse.cu", "comm.cu", "util.cu"]
 HOST_SOURCES = ["main.cpp", "Configuration.cpp", "InputParser.cpp", "StateFile.cpp", "TimeConverter.cpp", "TimeMeasurement.cpp",
                 "nBodyAlgorithm.cpp", "NaiveAlgorithm.cpp", "BarnesHutAlgorithm.cpp"]

@@ -389,6 +389,9 @@ static int inner_step(nb_ctx *ctx, int algorithm, double dt) {
 static bool graph_matches(const nb_ctx *ctx, int algorithm, double dt) {
     if (!ctx->step_graph || ctx->graph_algorithm != algorithm || ctx->graph_dt != dt || ctx->graph_n != ctx->n) return false;
     if (memcmp(&ctx->graph_cfg, &ctx->cfg, sizeof(nb_config)) != 0) return false;
+    // the graph froze the number of sort passes of its builds; the eager step just before this check chose from newer
+    // run statistics
+    if (algorithm == 1 && ctx->graph_sort_passes != ctx->bh.sort_passes) return false;
     const void *p[8];
     state_pointers(ctx, p);
     return memcmp(p, ctx->graph_ptrs, sizeof p) == 0;
@@ -462,6 +465,7 @@ static int capture_step_graph(nb_ctx *ctx, int algorithm, double dt) {
     ctx->graph_dt = dt;
     ctx->graph_n = ctx->n;
     ctx->graph_cfg = ctx->cfg;
+    ctx->graph_sort_passes = ctx->bh.sort_passes;
     memcpy(ctx->graph_ptrs, before, sizeof before);
     return NB_OK;
 }
@@ -775,7 +779,7 @@ namespace {
 struct HostTree {
     uint64_t n = 0, M = 0;
     std::vector<uint2> meta;
-    std::vector<double> com, msum;
+    std::vector<double> msum;
     std::vector<uint32_t> body_count, perm;
     double aabb[7];
 };
@@ -784,10 +788,9 @@ int fetch_tree(nb_ctx *ctx, HostTree &t) {
     NB_CHECK(nb_synchronize(ctx));
     t.n = ctx->n;
     t.M = b.num_nodes;
-    t.meta.resize(t.M); t.com.resize(4 * t.M); t.msum.resize(4 * t.M);
+    t.meta.resize(t.M); t.msum.resize(4 * t.M);
     t.body_count.resize(t.M); t.perm.resize(t.n);
     NB_CUDA(ctx, cudaMemcpy(t.meta.data(), b.meta, t.M * sizeof(uint2), cudaMemcpyDeviceToHost));
-    NB_CUDA(ctx, cudaMemcpy(t.com.data(), b.com, 4 * t.M * sizeof(double), cudaMemcpyDeviceToHost));
     NB_CUDA(ctx, cudaMemcpy(t.msum.data(), b.msum, 4 * t.M * sizeof(double), cudaMemcpyDeviceToHost));
     NB_CUDA(ctx, cudaMemcpy(t.body_count.data(), b.body_count, t.M * sizeof(uint32_t), cudaMemcpyDeviceToHost));
     NB_CUDA(ctx, cudaMemcpy(t.perm.data(), ctx->id, t.n * sizeof(uint32_t), cudaMemcpyDeviceToHost));  // slot -> body id
@@ -817,7 +820,7 @@ bool canon_rec(const HostTree &t, uint32_t node, int depth, uint64_t phi, uint64
         s.body[k] = leaf ? t.perm[m.y & NB_PAYLOAD_MASK] : (uint32_t) t.n;
         s.count[k] = t.body_count[node];
         s.edge[k] = edge; s.minx[k] = mnx; s.miny[k] = mny; s.minz[k] = mnz;
-        s.mass[k] = t.com[4 * (size_t) node + 3];
+        s.mass[k] = t.msum[4 * (size_t) node + 3];
         s.comx[k] = t.msum[4 * (size_t) node]; s.comy[k] = t.msum[4 * (size_t) node + 1]; s.comz[k] = t.msum[4 * (size_t) node + 2];
     }
     s.k++;

@@ -26,10 +26,12 @@
 //   5. centre of mass level by level, deepest first (one launch per depth, no atomics): a node sums its children in
 //      octant order (deterministic, bit-identical to the reference's order).
 #include <stdlib.h>
+#include <string.h>
 
 #include <algorithm>
 #include <cooperative_groups.h>
 
+#include "bh_accept.cuh"
 #include "scan_sort.cuh"
 
 #define NB_NONE 0xffffffffu
@@ -42,7 +44,8 @@ namespace {
 // ---- 1. AABB ----------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256)
 aabb_partial_kernel(const double *__restrict__ x, const double *__restrict__ y, const double *__restrict__ z,
-                    uint64_t n, double *__restrict__ partial /* [6][gridDim.x] */) {
+                    uint64_t n, double *__restrict__ partial /* [6][gridDim.x] */, uint32_t *__restrict__ flags) {
+    if (blockIdx.x == 0 && threadIdx.x == 0) flags[6] = 0;   // run statistic of this build's sort (tie_fix_kernel)
     // scratch starts at 0.0 like the reference's value-initialised per-work-item arrays (BarnesHutOctree.cpp:58-72)
     double mnx = 0, mny = 0, mnz = 0, mxx = 0, mxy = 0, mxz = 0;
     for (uint64_t i = (uint64_t) blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (uint64_t) gridDim.x * blockDim.x) {
@@ -69,8 +72,9 @@ aabb_partial_kernel(const double *__restrict__ x, const double *__restrict__ y, 
 }
 
 __global__ void __launch_bounds__(256)
-aabb_final_kernel(const double *__restrict__ partial, int n_partials, double *__restrict__ out /* 7 */) {
+aabb_final_kernel(const double *__restrict__ partial, int n_partials, double theta, double *__restrict__ out /* 8 + 64 */) {
     __shared__ double s[6][256];
+    __shared__ double s_edge;
     for (int c = 0; c < 6; ++c) {
         double v = 0.0;
         for (int i = threadIdx.x; i < n_partials; i += 256) {
@@ -110,7 +114,18 @@ aabb_final_kernel(const double *__restrict__ partial, int n_partials, double *__
         out[0] = min_x; out[1] = min_y; out[2] = min_z;
         out[3] = max_x; out[4] = max_y; out[5] = max_z;
         out[6] = maxEdgeLength;
+        s_edge = maxEdgeLength;
     }
+    // the walk's exact acceptance thresholds of this box, one per depth (bh_accept.cuh)
+    __syncthreads();
+    if (threadIdx.x < NB_ACCEPT_DEPTHS)
+        out[NB_ACCEPT_TABLE_OFFSET + threadIdx.x] = nb_accept_threshold(s_edge, theta, threadIdx.x);
+}
+
+// the same table for a theta that changed after the build (nb_set_theta between nb_bh_build and nb_bh_accel)
+__global__ void __launch_bounds__(NB_ACCEPT_DEPTHS)
+accept_table_kernel(double theta, double *__restrict__ aabb) {
+    aabb[NB_ACCEPT_TABLE_OFFSET + threadIdx.x] = nb_accept_threshold(aabb[6], theta, threadIdx.x);
 }
 
 // ---- 2. octant-path keys --------------------------------------------------------------------------------------------
@@ -169,7 +184,8 @@ unpack_kernel(const uint64_t *__restrict__ words, const uint64_t *__restrict__ k
 }
 
 #define NB_PACKED_KEY_SHIFT 23   /* a 5-pass packed sort orders the upper 40 of the 63 key bits: bits 23..62 */
-#define NB_PACKED_RUN_LIMIT 64   /* longer undecided runs make the host switch to the full 8-pass sort */
+#define NB_PACKED4_KEY_SHIFT 31  /* a 4-pass packed sort orders the upper 32: bits 31..62 (10 octree levels and a bit) */
+#define NB_PACKED_RUN_LIMIT 64   /* longer undecided runs make the host take more passes (4 -> 5 -> the full 8-pass sort) */
 
 // Bodies whose keys agree above `run_shift` form a run the sort left in slot order (run_shift = 23 after the packed
 // sort, 0 after the full sort: only bodies closer than edge * 2^-21 remain).  The head of each run orders it by the
@@ -183,13 +199,20 @@ tie_fix_kernel(uint64_t *__restrict__ hi_sorted, const double *__restrict__ x, c
     const uint64_t i = (uint64_t) blockIdx.x * blockDim.x + threadIdx.x;
     if (i + 1 >= n) return;
     const uint64_t hi_i = hi_sorted[i];
-    // statistic for the host's choice of sort: longest run of equal upper-40-bit prefixes, counted up to the limit + 1
+    // statistics for the host's choice of sort: longest run of equal upper-40-bit prefixes (flags[3]) and of equal
+    // upper-32-bit prefixes (flags[6]), counted up to the limit + 1
     {
-        const uint64_t k40 = hi_i >> NB_PACKED_KEY_SHIFT;
-        if ((hi_sorted[i + 1] >> NB_PACKED_KEY_SHIFT) == k40 && (i == 0 || (hi_sorted[i - 1] >> NB_PACKED_KEY_SHIFT) != k40)) {
-            uint32_t len = 2;
-            while (len <= NB_PACKED_RUN_LIMIT && i + len < n && (hi_sorted[i + len] >> NB_PACKED_KEY_SHIFT) == k40) ++len;
-            if (len > *(volatile uint32_t *) &flags[3]) atomicMax(&flags[3], len);
+        const uint64_t h_next = hi_sorted[i + 1], h_prev = i > 0 ? hi_sorted[i - 1] : ~hi_i;
+#pragma unroll
+        for (int w = 0; w < 2; ++w) {
+            const int sh = w ? NB_PACKED4_KEY_SHIFT : NB_PACKED_KEY_SHIFT;
+            uint32_t *stat = w ? &flags[6] : &flags[3];
+            const uint64_t k = hi_i >> sh;
+            if ((h_next >> sh) == k && (h_prev >> sh) != k) {
+                uint32_t len = 2;
+                while (len <= NB_PACKED_RUN_LIMIT && i + len < n && (hi_sorted[i + len] >> sh) == k) ++len;
+                if (len > *(volatile uint32_t *) stat) atomicMax(stat, len);
+            }
         }
     }
     const uint64_t k = hi_i >> run_shift;
@@ -656,7 +679,7 @@ int nbk_bh_reserve(nb_ctx *ctx) {
     NB_CHECK(nb_alloc(ctx, &b.body_count, cap_nodes));
     const size_t scratch = nbprim::os_scratch_elems(nb) + nbprim::scan_tiles_for(nb) + 64;
     NB_CHECK(nb_alloc(ctx, &b.hist, scratch));
-    NB_CHECK(nb_alloc(ctx, &b.aabb_dev, 8));
+    NB_CHECK(nb_alloc(ctx, &b.aabb_dev, NB_ACCEPT_TABLE_OFFSET + NB_ACCEPT_DEPTHS));
     NB_CHECK(nb_alloc(ctx, &b.aabb_partial, 6 * 1024));
     NB_CHECK(nb_alloc(ctx, &b.dev_flags, 8 + 1024));   // 8 flag words + per-SM tile counters of the traversal
     NB_CHECK(nb_alloc(ctx, &b.stat_totals, 8));
@@ -664,7 +687,7 @@ int nbk_bh_reserve(nb_ctx *ctx) {
         NB_CUDA(ctx, cudaMallocHost((void **) &b.stat_host, 4 * sizeof(uint32_t)));
         NB_CUDA(ctx, cudaEventCreateWithFlags(&b.stat_event, cudaEventDisableTiming));
     }
-    b.stat_pending = b.stat_known = b.long_runs = false;   // a new problem size: nothing is known about its distribution
+    b.stat_pending = b.stat_known = b.long_runs = b.long_runs32 = false;   // a new problem size: nothing is known about its distribution
     NB_CUDA(ctx, cudaMemsetAsync(b.dev_flags, 0, 8 * sizeof(uint32_t), ctx->stream));
     b.cap_bodies = n;
     b.cap_nodes = cap_nodes;
@@ -685,7 +708,7 @@ void nbk_bh_release(nb_ctx *ctx) {
         cudaFreeHost(b.stat_host); b.stat_host = nullptr;
         cudaEventDestroy(b.stat_event); b.stat_event = nullptr;
     }
-    b.stat_pending = b.stat_known = b.long_runs = false;
+    b.stat_pending = b.stat_known = b.long_runs = b.long_runs32 = false;
     b.cap_bodies = b.cap_nodes = 0;
     b.built = false;
 }
@@ -696,26 +719,41 @@ int nbk_bh_aabb(nb_ctx *ctx) {
     int blocks = (int) ((n + 255) / 256);
     if (blocks > 1024) blocks = 1024;
     if (blocks < 1) blocks = 1;
-    aabb_partial_kernel<<<blocks, 256, 0, ctx->stream>>>(ctx->x, ctx->y, ctx->z, n, b.aabb_partial);
+    aabb_partial_kernel<<<blocks, 256, 0, ctx->stream>>>(ctx->x, ctx->y, ctx->z, n, b.aabb_partial, b.dev_flags);
     NB_LAUNCH_CHECK(ctx);
-    aabb_final_kernel<<<1, 256, 0, ctx->stream>>>(b.aabb_partial, blocks, b.aabb_dev);
+    aabb_final_kernel<<<1, 256, 0, ctx->stream>>>(b.aabb_partial, blocks, ctx->cfg.theta, b.aabb_dev);
     NB_LAUNCH_CHECK(ctx);
+    b.accept_theta = ctx->cfg.theta;
     return NB_OK;
 }
 
-// Packed or full sort for this build (see nbk_bh_build).  The statistic of the latest finished build arrives through a
-// pinned word and an event; nothing here waits for the device.
-static bool bh_choose_packed_sort(nb_ctx *ctx) {
+// the walk calls this: the table must belong to the theta it is about to use
+int nbk_bh_accept_table(nb_ctx *ctx) {
+    nb_bh_state &b = ctx->bh;
+    if (memcmp(&b.accept_theta, &ctx->cfg.theta, sizeof(double)) == 0) return NB_OK;
+    accept_table_kernel<<<1, NB_ACCEPT_DEPTHS, 0, ctx->stream>>>(ctx->cfg.theta, b.aabb_dev);
+    NB_LAUNCH_CHECK(ctx);
+    b.accept_theta = ctx->cfg.theta;
+    return NB_OK;
+}
+
+// Passes of this build's sort: 8 = the full (key, slot) sort, 5 / 4 = packed words ordered on their upper 40 / 32 bits
+// (see nbk_bh_build).  The statistics of the latest finished build arrive through pinned words and an event; nothing
+// here waits for the device.
+static int bh_choose_sort_passes(nb_ctx *ctx) {
     nb_bh_state &b = ctx->bh;
     const int forced = ctx->cfg.reserved[6];
-    if (forced == 1) return false;
-    if (forced == 2) return true;
+    if (forced == 1) return 8;
+    if (forced == 2) return 5;
+    if (forced == 3) return 4;
     if (b.stat_pending && !ctx->capturing && cudaEventQuery(b.stat_event) == cudaSuccess) {
         b.stat_pending = false;
         b.stat_known = true;
         b.long_runs = b.stat_host[0] > NB_PACKED_RUN_LIMIT;
+        b.long_runs32 = b.stat_host[1] > NB_PACKED_RUN_LIMIT;
     }
-    return b.stat_known && !b.long_runs;
+    if (!b.stat_known || b.long_runs) return 8;
+    return b.long_runs32 ? 5 : 4;
 }
 
 int nbk_bh_build(nb_ctx *ctx) {
@@ -738,20 +776,25 @@ int nbk_bh_build(nb_ctx *ctx) {
         nb_timer_scope t(ctx, NB_T_KEYS_SORT);
         keys_kernel<<<g256, 256, 0, ctx->stream>>>(ctx->x, ctx->y, ctx->z, n, b.aabb_dev, b.key_hi);
         NB_LAUNCH_CHECK(ctx);
-        // Two forms of the same sort (cfg.reserved[6], sort_variant: 0 = chosen per build, 1 = full, 2 = packed):
-        //   packed: one 64-bit word {upper key bits | storage slot} per body, 5 one-sweep passes over its upper 40 bits
-        //           (13 octree levels), 16 B per body and pass; the few bodies that share a 13-level cell are then
-        //           ordered from their full keys by tie_fix_kernel;
+        // Forms of the same sort (cfg.reserved[6], sort_variant: 0 = chosen per build, 1 = full, 2 = packed with 5 passes,
+        // 3 = packed with 4 passes):
+        //   packed: one 64-bit word {upper key bits | storage slot} per body, one-sweep passes over its upper 40 bits
+        //           (13 octree levels) or 32 bits (10 levels), 16 B per body and pass; the bodies that share such a cell
+        //           (a few hundred pairs / a few hundred thousand pairs at N = 2^24) are then ordered from their full
+        //           keys by tie_fix_kernel;
         //   full:   (key, slot) pairs, 8 passes over all 63 key bits, 24 B per body and pass.
-        // Both end in the same order.  The packed form is what a step uses; the full form takes over when the previous
-        // build reported a long undecided run (a cluster far denser than the box: flags[3], read back asynchronously),
-        // and for the first build of a context, whose distribution nobody has seen yet.
-        const bool packed = bh_choose_packed_sort(ctx);
+        // All end in the same order.  A step uses the packed form with as few passes as the previous build's run
+        // statistics allow (flags[3] / flags[6]: the longest run of bodies that agree on 40 / 32 key bits, read back
+        // asynchronously): a cluster far denser than the box makes those runs long, and the single thread that orders a run
+        // slow.  The first build of a context, whose distribution nobody has seen yet, is always the full sort.
+        const int passes = bh_choose_sort_passes(ctx);
+        const bool packed = passes < 8;
+        b.sort_passes = passes;
         if (packed) {
             int idx_bits = 1;
             while ((1ull << idx_bits) < n) ++idx_bits;
             uint64_t *ws = nullptr;
-            NB_CHECK(nbprim::onesweep_sort_packed(ctx, b.key_hi, b.word_a, b.word_b, n, idx_bits, 5, b.hist, &ws));
+            NB_CHECK(nbprim::onesweep_sort_packed(ctx, b.key_hi, b.word_a, b.word_b, n, idx_bits, passes, b.hist, &ws));
             unpack_kernel<<<g256, 256, 0, ctx->stream>>>(ws, b.key_hi, n, idx_bits, b.perm, b.key_hi_alt);
             NB_LAUNCH_CHECK(ctx);
             hi_sorted = b.key_hi_alt;
@@ -761,7 +804,7 @@ int nbk_bh_build(nb_ctx *ctx) {
                                                  &perm_sorted, true));
         }
         tie_fix_kernel<<<g256, 256, 0, ctx->stream>>>(hi_sorted, ctx->x, ctx->y, ctx->z, b.aabb_dev, perm_sorted, n,
-                                                      packed ? NB_PACKED_KEY_SHIFT : 0, b.dev_flags);
+                                                      packed ? 63 - 8 * passes : 0, b.dev_flags);
         NB_LAUNCH_CHECK(ctx);
         // key_hi_alt / perm_alt are reused below: make the sorted data live in (key_hi, perm)
         if (hi_sorted != b.key_hi) { uint64_t *tk = b.key_hi; b.key_hi = b.key_hi_alt; b.key_hi_alt = tk; }
@@ -846,6 +889,7 @@ int nbk_bh_build(nb_ctx *ctx) {
     }
     if (!ctx->capturing && !b.stat_pending) {   // longest undecided run of this build -> the next builds' choice of sort
         NB_CUDA(ctx, cudaMemcpyAsync(b.stat_host, b.dev_flags + 3, sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
+        NB_CUDA(ctx, cudaMemcpyAsync(b.stat_host + 1, b.dev_flags + 6, sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
         NB_CUDA(ctx, cudaEventRecord(b.stat_event, ctx->stream));
         b.stat_pending = true;
     }

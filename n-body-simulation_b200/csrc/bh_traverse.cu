@@ -18,15 +18,12 @@
 //   * force: MUFU.RSQ64H seed + cubic Taylor refinement of (d2+eps2)^(-3/2) (see naive.cu).
 // Payload per visited node: 32 B {com xyz, mass} + 8 B {skip, leaf|body / depth} = 40 B.
 #include "common.cuh"
+#include "bh_accept.cuh"
 
 #include <algorithm>
 #include <type_traits>
 
 namespace {
-
-__device__ __forceinline__ double scale_pow2(double v, uint32_t depth) {  // v * 2^-depth, exact
-    return __hiloint2double(__double2hiint(v) - (int) (depth << 20), __double2loint(v));
-}
 
 // ---------------------------------------------------------------------------------------------------------------------
 // Production walk: acceptance test on the integer pipe, SM-local tile queues.
@@ -61,11 +58,13 @@ __device__ __forceinline__ double scale_pow2(double v, uint32_t depth) {  // v *
 // prefetch.global.L1 of the next node (98-102 ms); ticketed one-tile-per-warp assignment on a full grid (87 ms); one
 // straight-line accept/skip decision for leaves and cells instead of the leaf branch (88.9 ms).
 // ---------------------------------------------------------------------------------------------------------------------
-// the oracle's acceptance expression (BarnesHutAlgorithm.cpp:355-359) with correctly rounded operations
-__device__ __forceinline__ bool exact_accept(double dx, double dy, double dz, double edge0, uint32_t depth, double theta) {
+// The undecided band, and every depth where eps2 is not negligible: the reference's expression (BarnesHutAlgorithm.cpp:
+// 355-359) is monotone in the squared distance, so it is ONE comparison with the depth's exact threshold (bh_accept.cuh;
+// the table is computed with the reference's own operations once per build).  d2 is summed as the reference sums it,
+// without eps2 and without contraction.
+__device__ __forceinline__ bool exact_accept(double dx, double dy, double dz, const double *__restrict__ accept_thr, uint32_t depth) {
     const double d2o = __dadd_rn(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)), __dmul_rn(dz, dz));
-    const double rs = __ddiv_rn(1.0, __dsqrt_rn(d2o));
-    return __dmul_rn(scale_pow2(edge0, depth), rs) < theta;
+    return d2o > accept_thr[depth];
 }
 
 // What a warp does with the accelerations of its 32 bodies once their walk is finished (EPI).  The walk never reads
@@ -139,14 +138,27 @@ __device__ __noinline__ void walk_epilogue(const nb_walk_out &out, uint64_t b, d
     if (out.peers.world > 1) __threadfence_system();   // the peers read these stores after the next barrier
 }
 
+// resident 256-thread CTAs per SM the register budget is sized for: 5 -> 48 registers (40 warps), 6 -> 40 (48 warps)
+#ifndef NB_WALK_MIN_CTAS
+#define NB_WALK_MIN_CTAS 6
+#endif
+
 template <bool STATS, bool PERSIST, uint32_t RUN, int EPI>
-__global__ void __launch_bounds__(256, 5)
+__global__ void __launch_bounds__(256, NB_WALK_MIN_CTAS)
 bh_traverse_iw_kernel(const double4 *__restrict__ com, const uint2 *__restrict__ meta, const uint32_t *__restrict__ flags,
                       uint64_t n_bodies, const double *__restrict__ aabb, const double *__restrict__ sx, const double *__restrict__ sy,
                       const double *__restrict__ sz, uint64_t s_begin, uint64_t s_end, double theta, double eps2, double G,
                       const __grid_constant__ nb_walk_out out, uint32_t *__restrict__ visits,
                       unsigned long long *__restrict__ totals, uint32_t *__restrict__ tile_counters, uint32_t n_chunks,
                       double k1875) {
+    // The node array bases are used in every cursor step.  As plain kernel parameters ptxas re-loads them from the
+    // constant bank in every step (LDC.64 x 2); offset by a word that is always zero but comes from memory they are
+    // values only a register can hold.
+    {
+        const unsigned long long zero = flags[5];
+        asm volatile("add.u64 %0, %0, %2;\n\tadd.u64 %1, %1, %2;" : "+l"(com), "+l"(meta) : "l"(zero));
+        asm volatile("add.rn.f64 %0, %0, %1;" : "+d"(k1875) : "d"(__longlong_as_double((long long) zero)));   // + 0.0
+    }
     const double edge0 = aabb[6];
     const double ratio0 = (edge0 / theta) * (edge0 / theta);
     const bool scalable = ratio0 > 1e-200 && ratio0 < 1e200;   // theta == 0 or absurd boxes: always the exact branch
@@ -215,8 +227,12 @@ bh_traverse_iw_kernel(const double4 *__restrict__ com, const uint2 *__restrict__
         uint32_t cur = __reduce_min_sync(0xffffffffu, next);
         while (cur < n_nodes) {
             if (next == cur) {
-                const double4 c = com[cur];   // warp-uniform address: one broadcast transaction
-                const uint2 mt = meta[cur];
+                // warp-uniform address: broadcast transactions; sm_100 has 256-bit global loads (LDG.E.256)
+                double4 c;
+                asm("ld.global.nc.v4.f64 {%0,%1,%2,%3}, [%4];" : "=d"(c.x), "=d"(c.y), "=d"(c.z), "=d"(c.w) : "l"(com + cur));
+                uint2 mt;
+                asm("ld.global.nc.v2.u32 {%0,%1}, [%2];" : "=r"(mt.x), "=r"(mt.y) : "l"(meta + cur));
+                next = mt.x;   // accepted cells keep it; every other path overwrites it with cur + 1
                 const double dx = c.x - px, dy = c.y - py, dz = c.z - pz;
                 const double D = fma(dz, dz, fma(dy, dy, fma(dx, dx, eps2)));
                 // SUM_MASSES == 0 nodes are invisible in the reference (BarnesHutAlgorithm.cpp:349): massless bodies,
@@ -252,15 +268,14 @@ bh_traverse_iw_kernel(const double4 *__restrict__ com, const uint2 *__restrict__
                     if (STATS) nvis += 1u;
                     const bool guarded = GUARD && mt.y >= t_lim;
                     if (V > Whi && !guarded) {
-                        next = mt.x;      // a skip link points behind the node's subtree: always > cur
-                        force();
+                        force();          // next = skip link: points behind the node's subtree, always > cur
                     } else if (V < Wlo && !guarded) {
                         next = cur + 1;
                     } else {
                         // undecided, or a depth where eps2 matters: the oracle's exact expression, no contraction
-                        const bool accept = exact_accept(dx, dy, dz, edge0, mt.y >> NB_DEPTH_SHIFT, theta);
-                        next = accept ? mt.x : cur + 1;
+                        const bool accept = exact_accept(dx, dy, dz, aabb + NB_ACCEPT_TABLE_OFFSET, mt.y >> NB_DEPTH_SHIFT);
                         if (accept) force();
+                        else next = cur + 1;
                     }
                 }
             }
@@ -390,6 +405,7 @@ int nbk_bh_accel_fused(nb_ctx *ctx, uint64_t s_begin, uint64_t s_end, int epilog
     if (!b.built) return nb_fail(ctx, NB_ERR_INVALID, "nb_bh_accel: call nb_bh_build first");
     if (dynamic_slices && to_peers) { s_begin = 0; s_end = ctx->n; }   // the kernel reads its slice from dyn_bounds: size the grid for any
     if (s_end <= s_begin) return NB_OK;
+    NB_CHECK(nbk_bh_accept_table(ctx));   // theta may have changed since the build
     if (to_peers && !ctx->p2p_ok) return nb_fail(ctx, NB_ERR_INVALID, "walk with peer stores: peer slabs are not mapped");
     int threads = ctx->cfg.wg_size_barnes_hut;  // --wg_size_barnes_hut -> CTA size (multiple of 32, <= 256)
     if (threads < 32) threads = 32;

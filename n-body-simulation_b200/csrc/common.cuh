@@ -59,14 +59,17 @@ struct nb_bh_state {
     int walk_ctas_per_sm = 0, walk_ctas_threads = 0;         // occupancy of the persistent walk (cached)
     int com_ctas_per_sm = 0;                                 // occupancy of the cooperative centre-of-mass kernel (cached)
     // device scalars
-    double *aabb_dev = nullptr;                              // 7 doubles: min xyz, max xyz, edge
+    double *aabb_dev = nullptr;                              // min xyz, max xyz, edge, unused, then the walk's acceptance threshold of
+                                                             // every depth (bh_accept.cuh), computed for accept_theta
+    double accept_theta = 0;
     double *aabb_partial = nullptr;
     uint32_t *dev_flags = nullptr;                           // [0] error bits of the latest build (1 depth, 2 pool), [1] internal node count,
                                                              // [2] max depth, [3] longest run the packed sort leaves undecided (capped),
                                                              // [4] error bits of all builds since they were last reported (sticky)
-    uint32_t *stat_host = nullptr;                           // pinned copy of dev_flags[3] of the latest finished build
+    uint32_t *stat_host = nullptr;                           // pinned copies of dev_flags[3] and [6] of the latest finished build
     cudaEvent_t stat_event = nullptr;
-    bool stat_pending = false, stat_known = false, long_runs = false;
+    bool stat_pending = false, stat_known = false, long_runs = false, long_runs32 = false;
+    int sort_passes = 0;                                     // passes of the latest build's sort (8 = the full sort)
     uint64_t cap_bodies = 0, cap_nodes = 0;
     uint64_t num_nodes = 0, num_internal = 0;
     uint32_t max_depth = 0;
@@ -130,6 +133,7 @@ struct nb_ctx {
     double graph_dt = 0;
     uint64_t graph_n = 0;
     nb_config graph_cfg = {};
+    int graph_sort_passes = 0;        // sort passes of the builds inside the graph (chosen at capture time)
     const void *graph_ptrs[8] = {};
     uint64_t graph_launches = 0;      // kernel launches one replay stands for
     bool graph_unusable = false;      // the period-two assumption did not hold: stay on the eager path
@@ -208,6 +212,7 @@ int nbk_fp64_peak(nb_ctx *ctx, double *tflops);
 int nbk_bh_reserve(nb_ctx *ctx);
 void nbk_bh_release(nb_ctx *ctx);
 int nbk_bh_aabb(nb_ctx *ctx);
+int nbk_bh_accept_table(nb_ctx *ctx);           // acceptance thresholds for the current theta (no-op when up to date)
 int nbk_bh_build(nb_ctx *ctx);
 int nbk_bh_accel(nb_ctx *ctx, uint64_t s_begin, uint64_t s_end);
 int nbk_unpermute(nb_ctx *ctx, int count, const double *const *src, double *const *dst);

@@ -295,13 +295,14 @@ def test_deep_tree_uses_second_key_word(nb, oracle):
     ctx.close()
 
 
-@pytest.mark.parametrize("sort_variant", [0, 1, 2])
+@pytest.mark.parametrize("sort_variant", [0, 1, 2, 3])
 @pytest.mark.parametrize("n_cluster", [40, 700])
 def test_dense_cluster_in_a_wide_box(nb, oracle, sort_variant, n_cluster):
     """A cluster 2^-18 of the box wide plus far outliers: every cluster body shares its first ~17 octree levels, i.e. all 40
-    key bits the packed sort orders, so the whole cluster is one run the sort leaves undecided (tie_fix_kernel orders it
-    from the full keys; beyond 64 bodies per run the per-build choice goes back to the full sort).  Same canonical tree,
-    same order, over several builds, whichever form sorts."""
+    key bits the packed sort orders (or all 32 of its 4-pass form, sort_variant 3), so the whole cluster is one run the
+    sort leaves undecided (tie_fix_kernel orders it from the full keys; beyond 64 bodies per run the per-build choice goes
+    back to more passes and finally to the full sort).  Same canonical tree, same order, over several builds, whichever
+    form sorts."""
     rng = np.random.default_rng(77)
     m0, x0, y0, z0, *_ = nb.generators.uniform_sphere(200, seed=13)
     xc = 0.3 + 4e-6 * rng.random(n_cluster); yc = -0.2 + 4e-6 * rng.random(n_cluster); zc = 0.1 + 4e-6 * rng.random(n_cluster)
@@ -400,22 +401,23 @@ def test_bh_walk_forms_agree(nb, oracle, n, gen):
 @pytest.mark.parametrize("n,gen", [(1, "plummer"), (2047, "plummer"), (2049, "uniform_sphere"), (300001, "plummer"),
                                    (1 << 21, "uniform_sphere")])
 def test_sort_forms_give_the_same_order(nb, oracle, n, gen):
-    """The two forms of the build's sort -- packed {upper 40 key bits | slot} words, 5 one-sweep passes, ties ordered from
-    the full keys (sort_variant 2) and (key, slot) pairs, 8 passes over all 63 key bits (1) -- and the per-build choice
-    between them (0: full for the first build, packed afterwards) end in the same order: identical in-order permutation
+    """The forms of the build's sort -- packed {upper key bits | slot} words, 5 or 4 one-sweep passes over 40 or 32 key
+    bits, ties ordered from the full keys (sort_variant 2, 3) and (key, slot) pairs, 8 passes over all 63 key bits (1) --
+    and the per-build choice between them (0: full for the first build, then as few passes as the run statistics of the
+    previous build allow) end in the same order: identical in-order permutation
     (BarnesHutOctree.cpp:550-613), identical storage order, identical accelerations -- also over repeated builds of
     moving bodies (the look-back status table is reused) and for tile counts of 1, 2 and many.  The permutation must be
     the oracle's."""
     m, x, y, z, vx, vy, vz = getattr(nb.generators, gen)(n, seed=33)
     got = {}
-    for sv in (0, 1, 2):
+    for sv in (0, 1, 2, 3):
         c = nb.Context(device=0, theta=0.5, sort_variant=sv)
         c.set_bodies(m, x, y, z, vx, vy, vz)
         for _ in range(3):
             c.leapfrog_part1(0.01); c.bh_build(); c.bh_accel(); c.leapfrog_part2(0.01)
         got[sv] = (np.asarray(c.bh_sorted_bodies()), np.stack(c.accelerations()), np.stack(c.positions()))
         c.close()
-    for sv in (1, 2):
+    for sv in (1, 2, 3):
         for a, b in zip(got[0], got[sv]):
             assert np.array_equal(a, b)
     if n <= 300001:

@@ -25,6 +25,7 @@ for wv in variants:
             base = a
         same = bool(np.array_equal(a, base))
         err = float(np.abs(a - base).max() / np.abs(base).max())
-        print("N=%d %s walk_variant=%d wg=%d traversal ms: %s  identical=%s maxdiff=%.2e" %
-              (n, gen, wv, wg, " ".join("%.2f" % t for t in ts), same, err), flush=True)
+        print("%s N=%d %s walk_variant=%d wg=%d traversal ms: %s  identical=%s maxdiff=%.2e sum|a|=%.17g" %
+              (os.environ.get("NB_LIB", "current"), n, gen, wv, wg, " ".join("%.2f" % t for t in ts), same, err,
+               float(np.abs(a).sum())), flush=True)
         c.close()
