@@ -10,10 +10,11 @@
 //     same order (no warp-vote widening of the acceptance test), but node loads are warp-uniform broadcasts;
 //   * bodies are processed in sorted (Morton / DFS) order so neighbouring lanes share almost all of their lists;
 //   * centre of mass is pre-divided in the COM pass (same IEEE quotient the reference computes per visit);
-//   * acceptance test edge*rsqrt(d2) < theta is decided without memory access from the node's depth: the production
-//     kernel (bh_traverse_iw_kernel) compares the high word of d2 + eps2 with hiword((edge_0/theta)^2) - (depth << 21)
-//     on the integer pipe; the vanishing band around the threshold is re-evaluated with correctly rounded sqrt /
-//     reciprocal / multiply, i.e. exactly the oracle's expression, so the interaction set is identical;
+//   * acceptance test edge*rsqrt(d2) < theta is decided without memory access from the node's depth: the kernel
+//     compares the high word of d2 + eps2 with hiword((edge_0/theta)^2) - (depth << 21) on the integer pipe; the
+//     vanishing band around the threshold is decided by ONE fp64 compare with the depth's exact threshold
+//     (bh_accept.cuh: the reference's expression is monotone in d2, the threshold is found with the reference's own
+//     correctly rounded operations once per build), so the interaction set is identical;
 //   * production launches are persistent: warps draw 32-body tiles from SM-local queues (see the kernel's comment);
 //   * force: MUFU.RSQ64H seed + cubic Taylor refinement of (d2+eps2)^(-3/2) (see naive.cu).
 // Payload per visited node: 32 B {com xyz, mass} + 8 B {skip, leaf|body / depth} = 40 B.
@@ -28,31 +29,37 @@ namespace {
 // ---------------------------------------------------------------------------------------------------------------------
 // Production walk: acceptance test on the integer pipe, SM-local tile queues.
 //
-// Same traversal and the same interaction sets as bh_traverse_kernel above (kept as walk_variant 5 for A/B runs).
 //   * D = dx^2 + dy^2 + dz^2 + eps2 is ONE fma chain (eps2 folded into the first term) and serves both the acceptance
 //     test and the force;
 //   * positive doubles order like their bit patterns, so "D > (edge_d/theta)^2" is decided by comparing HIGH WORDS:
 //     W_d = hiword((edge_0/theta)^2) - (depth << 21)  (the edge halves exactly per level); accept when
-//     hiword(D) >= W_d + 2, open when hiword(D) <= W_d - 2 (evaluated as V = hiword(D) + (depth << 21) against W_0 +- 1).  The band in between (relative width 2^-19) and every
-//     depth for which eps2 is not negligible against (edge_d/theta)^2 take the oracle's exact expression
-//     (BarnesHutAlgorithm.cpp:355-359) with correctly rounded operations, so the decision is the reference's.  No
-//     per-depth fp64 thresholds, nothing spills under the 48-register budget (40 warps per SM);
+//     hiword(D) >= W_d + 2, open when hiword(D) <= W_d - 2 (evaluated as V = hiword(D) + (depth << 21 | rank) against
+//     W_0 + 8 and W_0 - 1).  The band in between (relative width 10^-5) and every depth for which eps2 is not negligible
+//     against (edge_d/theta)^2 take exact_accept() below, so the decision is the reference's;
 //   * PERSIST: the grid only fills the machine and every WARP draws 32-body tiles from a queue that belongs to the SM
 //     it runs on (queue c owns runs of RUN consecutive tiles of the sorted order, interleaved with the other queues'
-//     runs; a warp whose queue is empty steals from the following queues).  The ~40 warps resident on an SM therefore
+//     runs; a warp whose queue is empty steals from the following queues).  The 48 warps resident on an SM therefore
 //     walk neighbouring bodies at the same time and share the node records they pull into that SM's L1 -- the hardware
 //     block scheduler would hand an SM blocks that are 148 blocks apart -- while all SMs stay inside one moving window
 //     of the tree (L2), and no CTA is ever re-launched.  ncu at N = 2^24: L1 hit rate 65 % -> 73 %, warps active
 //     57 % -> 62 %, 89.6 ms -> 84.2 ms.  tile_counters: one uint32 per queue, zeroed before the launch.
 //     The queue bookkeeping must not add live values to the cursor loop: with RUN as a run-time argument ptxas spilled
 //     two loop invariants and the walk fell back to 90 ms, hence the template constant.
-//   * the cursor step is issue bound, so every instruction taken out of it shows: 1.875 of the Taylor term arrives as a
-//     kernel parameter (one LDC instead of two moves that ptxas re-materialised per node under the register budget), the
-//     acceptance test is ONE multiply-add V = hiword(D) + (depth << 21) and two compares against W_0 + 1 and W_0 - 1
-//     (kept opaque so they are not re-derived per node), the skip link is used as it is (it always points behind the
-//     node's subtree, no max), and the depth guard t >= t_lim is compiled out of the loop when the deepest level of
-//     THIS tree (flags[2]) cannot reach it.  56 -> 45 SASS instructions per accepted cell, 84.2 -> 77.2 ms at N = 2^24,
-//     bit-identical results.
+//   * the cursor step is bound by issue slots and by the latency the resident warps can hide, so both every instruction
+//     taken out of it and every warp added show.  Round 1: the acceptance test is ONE add V = hiword(D) + (depth << 21)
+//     and two compares against W_0 + 8 and W_0 - 1 (kept opaque so they are not re-derived per node), the skip link is
+//     used as it is (it always points behind the node's subtree, no max), the depth guard t >= t_lim is compiled out of
+//     the loop when the deepest level of THIS tree (flags[2]) cannot reach it: 56 -> 45 SASS instructions per accepted
+//     cell.  Round 2: accept / open / undecided as three paths with their own copy of the force arithmetic (41); then
+//       - the node's {com, mass} is one 256-bit load (LDG.E.256, sm_100) instead of two 128-bit ones            (40)
+//       - the skip link is loaded straight into `next`; the paths that do not follow it overwrite it              (39)
+//       - the exact re-test is a compare with a table entry instead of sqrt + division: no slow-path calls, six
+//         registers fewer, nothing spills, and the register allocator stops re-loading loop invariants
+//       - the bases of the two node arrays and the constant 1.875 are made values that only registers can hold (an
+//         offset that is always zero but comes from memory): 3 x LDC per step gone                                (36)
+//       - what is left fits 40 registers (__launch_bounds__(256, 6)): 48 instead of 40 resident warps per SM.
+//     N = 2^24, theta = 0.5: 72.7 ms (41 instructions, 40 warps) -> 69.5 ms (36, 40) -> 65.4 ms (36, 48), bit-identical
+//     results (profiles/walk36_ab_r02.log).
 // Explored on top of this and rejected (N = 2^24, theta = 0.5, all parity-green): issuing the next node's loads before
 // the force arithmetic (software pipelining: 95 ms, the 12 extra live registers cost 20 % of the resident warps);
 // prefetch.global.L1 of the next node (98-102 ms); ticketed one-tile-per-warp assignment on a full grid (87 ms); one
