@@ -56,9 +56,9 @@ FP64_LANES_PER_SM = 64.0             # DP pipe: 64 lanes per SM and clock (one D
 NAIVE_TILE = 256                     # --block_size used for the benchmark (shared-memory tile length)
 # dram__bytes_read.sum + dram__bytes_write.sum per launch, NOT measured in this run: from the `ncu --set full` captures
 # summarised under profiles/ (naive: N = 2^20, profiles/naive_accel_r02.txt -- 444 MB of the writes are the per-segment
-# partial sums; walk: N = 2^24, acceleration-only form, profiles/bh_step_r02.txt)
-NCU_TRAFFIC_BYTES = {("naive", 1 << 20): 168.282112e6 + 443.659520e6, ("bh", 1 << 24): 2.533143e9 + 399.558912e6}
-NCU_TRAFFIC_SOURCE = {"naive": "profiles/naive_accel_r02.txt", "bh": "profiles/bh_step_r02.txt"}
+# partial sums; walk: N = 2^24, acceleration-only form, profiles/bh_traverse_r02f.txt)
+NCU_TRAFFIC_BYTES = {("naive", 1 << 20): 168.282112e6 + 443.659520e6, ("bh", 1 << 24): 2.479455e9 + 398.411776e6}
+NCU_TRAFFIC_SOURCE = {"naive": "profiles/naive_accel_r02.txt", "bh": "profiles/bh_traverse_r02f.txt"}
 PARITY_TOL = 1e-10
 
 
